@@ -1,0 +1,158 @@
+/* C ABI of a compiled SODA program for NVIDIA B200 (sm_100a).
+ *
+ * `sodac prog.soda --cuda-lib libprog.so` builds one shared library per SODA
+ * program.  Every such library exports the same symbols (declared here), so a
+ * host binds them with dlopen/ctypes/cgo without knowing the program, plus one
+ * program-named entry point `soda_cuda_<app>` whose argument list mirrors the
+ * host wrapper the reference generates:
+ *
+ *   reference (src/soda/codegen/frt/host.py:62-89):
+ *     int soda::app::<app>(const T* var_<in>_ptr, const int32_t var_<in>_extent[D],
+ *                          const int32_t var_<in>_stride[D], const int32_t var_<in>_min[D],
+ *                          ... the same four per output (non-const ptr) ...,
+ *                          const char* bitstream, int burst_width, int tile_size_<d>...,
+ *                          int unroll_factor);
+ *   this library:
+ *     int soda_cuda_<app>(const T* var_<in>_ptr, const int32_t* var_<in>_extent,
+ *                         const int32_t* var_<in>_stride, const int32_t* var_<in>_min,
+ *                         ... the same four per output ...,
+ *                         const soda_cuda_opts* opts);
+ *
+ *   `bitstream`, `burst_width`, `tile_size_*`, `unroll_factor` select an FPGA
+ *   image and its stream layout; they have no meaning on a GPU and are replaced
+ *   by `opts` (may be NULL).  As in the reference, the call blocks, returns 0 on
+ *   success, the caller owns every array, only the valid interior of each output
+ *   is written (src/soda/codegen/frt/host.py:357-374,422-424) and `min` is
+ *   accepted but not used (the reference only logs it, :251-262).
+ *
+ * Arrays are dense in dimension 0 (stride[0] == 1); stride[d] is the distance
+ * in elements between consecutive indices of dimension d.
+ *
+ * Error convention: 0 = success; otherwise a soda_cuda_status value, and
+ * soda_cuda_last_error() returns a message for the calling thread.  No
+ * exception crosses this boundary.
+ */
+#ifndef SODA_CUDA_H_
+#define SODA_CUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SODA_CUDA_MAX_DIM 3
+#define SODA_CUDA_MAX_TENSORS 8
+#define SODA_CUDA_MAX_PASSES 1024
+
+typedef enum soda_cuda_status {
+  SODA_CUDA_OK = 0,
+  SODA_CUDA_BAD_ARGUMENT = 1,
+  SODA_CUDA_CUDA_ERROR = 2,
+  SODA_CUDA_UNSUPPORTED = 3,
+  SODA_CUDA_OUT_OF_MEMORY = 4
+} soda_cuda_status;
+
+typedef enum soda_cuda_dtype {
+  SODA_CUDA_U8 = 0, SODA_CUDA_I8 = 1, SODA_CUDA_U16 = 2, SODA_CUDA_I16 = 3,
+  SODA_CUDA_U32 = 4, SODA_CUDA_I32 = 5, SODA_CUDA_U64 = 6, SODA_CUDA_I64 = 7,
+  SODA_CUDA_F32 = 8, SODA_CUDA_F64 = 9
+} soda_cuda_dtype;
+
+/* Run-time options; zero-initialise and set struct_size = sizeof(soda_cuda_opts). */
+typedef struct soda_cuda_opts {
+  int32_t struct_size;
+  int32_t device;        /* CUDA device ordinal; -1 = current device */
+  void* stream;          /* cudaStream_t; NULL = the default stream */
+  int32_t segment;       /* output slices per CTA along the streamed dimension; 0 = auto */
+  int32_t reserved[5];
+} soda_cuda_opts;
+
+/* One pass = one HBM round trip = `time_block` fused iterations. */
+typedef struct soda_cuda_pass_info {
+  int32_t time_block;
+  /* how far the pass output depends on the pass input, per dimension:
+   * output cell p reads input cells p+reach_lo .. p+reach_hi (reach_lo <= 0) */
+  int32_t reach_lo[SODA_CUDA_MAX_DIM];
+  int32_t reach_hi[SODA_CUDA_MAX_DIM];
+  int32_t threads_per_cta;
+  int32_t smem_bytes;
+  int32_t cells_per_lane;
+  int32_t strip_cells;      /* cells per warp in dimension 0 */
+  int32_t valid_cells[2];   /* stored cells per strip / tile in dims 0 (and 1) */
+} soda_cuda_pass_info;
+
+typedef struct soda_cuda_program_info {
+  const char* app_name;
+  const char* soda_source;     /* the program this library was compiled from */
+  int32_t dim;
+  int32_t iterate;
+  int32_t num_inputs;
+  int32_t num_outputs;
+  const char* input_names[SODA_CUDA_MAX_TENSORS];
+  const char* output_names[SODA_CUDA_MAX_TENSORS];
+  int32_t input_dtypes[SODA_CUDA_MAX_TENSORS];   /* soda_cuda_dtype */
+  int32_t output_dtypes[SODA_CUDA_MAX_TENSORS];
+  /* valid box of output o on a grid of `extent`:
+   *   [final_lo[o][d], extent[d] - final_hi[o][d])   per dimension d */
+  int32_t final_lo[SODA_CUDA_MAX_TENSORS][SODA_CUDA_MAX_DIM];
+  int32_t final_hi[SODA_CUDA_MAX_TENSORS][SODA_CUDA_MAX_DIM];
+  int32_t num_passes;
+  int32_t strict_fp;            /* 1: compiled with --fmad=false (bit-exact vs g++) */
+  int32_t algorithmic_bytes_per_cell_per_pass;
+} soda_cuda_program_info;
+
+typedef struct soda_cuda_plan soda_cuda_plan;   /* opaque */
+
+/* Program description.  Replaces the `// stencil window size` / kStencilDim
+ * constants the reference prints into the host (src/soda/codegen/frt/host.py:686-699). */
+int soda_cuda_info(soda_cuda_program_info* info);
+int soda_cuda_get_pass_info(int32_t pass_index, soda_cuda_pass_info* info);
+
+/* Message for the last non-zero status returned to this thread. */
+const char* soda_cuda_last_error(void);
+
+/* One-shot, host arrays in / host arrays out; host<->device copies included.
+ * Generic form of soda_cuda_<app>: per-tensor arrays instead of named arguments.
+ * Replaces soda::app::<app> (src/soda/codegen/frt/host.py:62-431). */
+int soda_cuda_run_host(const void* const* in_ptrs, const int32_t* const* in_strides,
+                       void* const* out_ptrs, const int32_t* const* out_strides,
+                       const int32_t* extent, const soda_cuda_opts* opts);
+
+/* A plan owns the device-side scratch (ping-pong buffers, staging copies) for
+ * one grid extent, like the tiled buffers the reference wrapper allocates per
+ * call (src/soda/codegen/frt/host.py:149-179), but reusable across calls. */
+int soda_cuda_plan_create(const int32_t* extent, const soda_cuda_opts* opts,
+                          soda_cuda_plan** plan);
+int soda_cuda_plan_destroy(soda_cuda_plan* plan);
+
+/* Host arrays through a plan (pinned or pageable memory). */
+int soda_cuda_plan_run_host(soda_cuda_plan* plan,
+                            const void* const* in_ptrs, const int32_t* const* in_strides,
+                            void* const* out_ptrs, const int32_t* const* out_strides);
+
+/* Device arrays through a plan: all `iterate` iterations, asynchronous on the
+ * plan's stream.  pitches[t][0] = elements between rows, pitches[t][1] = between
+ * planes (3-D).  Base addresses and row pitches must be 16-byte aligned. */
+int soda_cuda_plan_run_device(soda_cuda_plan* plan,
+                              const void* const* d_in, const int64_t (*in_pitches)[2],
+                              void* const* d_out, const int64_t (*out_pitches)[2]);
+
+/* One pass on caller-owned device buffers (used by the multi-GPU slab runtime,
+ * which exchanges halos between passes).  `extent` is the extent of the local
+ * arrays; outputs are written inside [box_lo[o], box_hi[o]) only. */
+int soda_cuda_run_pass(int32_t pass_index, const int32_t* extent,
+                       const void* const* d_in, const int64_t (*in_pitches)[2],
+                       void* const* d_out, const int64_t (*out_pitches)[2],
+                       const int32_t (*box_lo)[SODA_CUDA_MAX_DIM],
+                       const int32_t (*box_hi)[SODA_CUDA_MAX_DIM],
+                       const soda_cuda_opts* opts);
+
+/* Number of kernel launches issued by this library since it was loaded. */
+int64_t soda_cuda_launch_count(void);
+
+#ifdef __cplusplus
+}  /* extern "C" */
+#endif
+
+#endif  /* SODA_CUDA_H_ */

@@ -1,0 +1,87 @@
+"""nvcc driver: generated program text -> in-tree shared library for sm_100a."""
+import hashlib
+import os
+import shutil
+import subprocess
+from typing import Dict, List, Optional
+
+from soda_b200.codegen.cuda import emit
+
+PACKAGE_DIR = os.path.dirname(
+    os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+CSRC_DIR = os.path.join(PACKAGE_DIR, 'csrc')
+INCLUDE_DIR = os.path.join(os.path.dirname(PACKAGE_DIR), 'include')
+BUILD_DIR = os.path.join(PACKAGE_DIR, '_build')
+
+ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
+
+
+def nvcc_path() -> str:
+  path = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+  if not os.path.exists(path):
+    raise RuntimeError('nvcc not found: the CUDA backend needs the CUDA toolkit')
+  return path
+
+
+def nvcc_flags(strict_fp: bool = True, extra: Optional[List[str]] = None):
+  flags = ['-std=c++17', '-O3', '-lineinfo', '-shared', '-Xcompiler', '-fPIC'
+          ] + ARCH_FLAGS
+  # the reference's results are those of g++ without FMA contraction; keep
+  # float arithmetic un-contracted unless the user opts out
+  flags.append('--fmad=false' if strict_fp else '--fmad=true')
+  flags += ['-I', CSRC_DIR, '-I', INCLUDE_DIR]
+  return flags + list(extra or [])
+
+
+def _headers_digest() -> str:
+  digest = hashlib.sha1()
+  for directory in (CSRC_DIR, INCLUDE_DIR):
+    for name in sorted(os.listdir(directory)):
+      if name.endswith(('.cuh', '.h')):
+        with open(os.path.join(directory, name), 'rb') as fp:
+          digest.update(fp.read())
+  return digest.hexdigest()
+
+
+def library_path(stencil, source: str, strict_fp: bool) -> str:
+  digest = hashlib.sha1(
+      (source + _headers_digest() + str(strict_fp)).encode()).hexdigest()[:12]
+  return os.path.join(BUILD_DIR,
+                      'libsoda_%s_%s.so' % (stencil.app_name, digest))
+
+
+def build_library(stencil,
+                  time_block: Optional[int] = None,
+                  options: Optional[Dict] = None,
+                  output: Optional[str] = None,
+                  keep_source: Optional[str] = None,
+                  verbose: bool = False) -> str:
+  """Generates and compiles the program; returns the path of the .so.
+
+  Libraries are cached in ``soda_b200/_build`` keyed by the hash of the
+  generated source, the template headers and the FP mode (the reference caches
+  its slow build products by ``str(stencil)`` in the same spirit, reference:
+  src/soda/optimization/cluster.py:111-121).
+  """
+  options = dict(options or {})
+  strict_fp = not options.get('fast_fp')
+  source = emit.emit_program(stencil, time_block=time_block, options=options)
+  os.makedirs(BUILD_DIR, exist_ok=True)
+  lib = output or library_path(stencil, source, strict_fp)
+  src_path = keep_source or (os.path.splitext(lib)[0] + '.cu')
+  if output is None and os.path.exists(lib):
+    return lib
+  with open(src_path, 'w') as fp:
+    fp.write(source)
+  tmp = '%s.%d.tmp' % (lib, os.getpid())
+  cmd = [nvcc_path()] + nvcc_flags(strict_fp) + ['-o', tmp, src_path]
+  if verbose:
+    cmd.insert(1, '-Xptxas')
+    cmd.insert(2, '-v')
+  result = subprocess.run(cmd, capture_output=True, text=True)
+  if result.returncode != 0:
+    raise RuntimeError('nvcc failed:\n%s\n%s' % (' '.join(cmd), result.stderr))
+  if verbose:
+    print(result.stderr)
+  os.replace(tmp, lib)
+  return lib

@@ -1,0 +1,359 @@
+"""Specialises the hand-written CUDA templates for one SODA program.
+
+The generated translation unit contains *only*
+
+* one functor per statement: the statement's expression printed from the IR,
+  with every tensor load spelled ``a.template ld<slot, dx, dy, ds>()``;
+* constexpr plan tables per pass variant (``soda::NodeDesc`` rows, halos, lags);
+* the static program description consumed by the runtime (names, dtypes, valid
+  boxes, pass schedule) and the program-named C entry point.
+
+Tiling, pipelines, sliding windows, shuffles, stores and the host runtime are
+the hand-written headers under ``soda_b200/csrc``; nothing kernel-shaped is
+emitted here (BASELINE.json north_star: "specialised from the IR by
+instantiating a hand-written template rather than by emitting free-form
+kernels").  The reference's counterpart is the HLS kernel printer
+(reference: src/soda/codegen/xilinx/hls_kernel.py:338-971), which does print
+free-form modules.
+"""
+import math
+from typing import Dict, List, Optional, Sequence
+
+from soda_b200 import ir, util
+from soda_b200.codegen.cuda import plan as planner
+
+DTYPE_CODES = {
+    'uint8': 'SODA_CUDA_U8',
+    'int8': 'SODA_CUDA_I8',
+    'uint16': 'SODA_CUDA_U16',
+    'int16': 'SODA_CUDA_I16',
+    'uint32': 'SODA_CUDA_U32',
+    'int32': 'SODA_CUDA_I32',
+    'uint64': 'SODA_CUDA_U64',
+    'int64': 'SODA_CUDA_I64',
+    'float': 'SODA_CUDA_F32',
+    'double': 'SODA_CUDA_F64',
+}
+
+_HELPERS = r'''
+namespace soda_gen {
+template <typename T> __host__ __device__ __forceinline__ T soda_min(T a, T b) { return b < a ? b : a; }
+template <typename T> __host__ __device__ __forceinline__ T soda_max(T a, T b) { return a < b ? b : a; }
+template <typename T> __host__ __device__ __forceinline__ T soda_abs(T a) { return a < 0 ? T(-a) : a; }
+// integer division by zero can only happen on cells that are never stored
+template <typename T> __host__ __device__ __forceinline__ T soda_div(T a, T b) { return b == 0 ? T(0) : T(a / b); }
+template <typename T> __host__ __device__ __forceinline__ T soda_mod(T a, T b) { return b == 0 ? T(0) : T(a % b); }
+}  // namespace soda_gen
+'''
+
+
+class _FunctorPrinter(ir.CPrinter):
+  """CPrinter that guards integer ``/`` and ``%`` against zero divisors (they
+  occur only in never-stored halo cells) - C++ semantics are unchanged for
+  non-zero divisors."""
+
+  def __call__(self, node):
+    if isinstance(node, ir.MulDiv) and not node.singleton and \
+        not ir.result_type(node).is_float and \
+        any(op in ('/', '%') for op in node.operator):
+      text = self(node.operand[0])
+      t = ir.result_type(node.operand[0])
+      for operator, operand in zip(node.operator, node.operand[1:]):
+        t = ir.common_type(t, ir.result_type(operand))
+        rhs = self(operand)
+        if operator == '*':
+          text = '({} * {})'.format(text, rhs)
+        else:
+          func = 'soda_gen::soda_div' if operator == '/' else \
+              'soda_gen::soda_mod'
+          text = '{}<{}>({}, {})'.format(func, t.c_type, text, rhs)
+      return text
+    return super().__call__(node)
+
+
+def _functor(desc: planner.StageDesc, dim: int) -> List[str]:
+  stmt = desc.stmt
+  slots = {name: k for k, name in enumerate(desc.slots)}
+  st_idx = stmt.ref.idx
+
+  def ref_printer(ref: ir.Ref) -> str:
+    delta = [a - b for a, b in zip(ref.idx, st_idx)]
+    dx = delta[0]
+    dy = delta[1] if dim == 3 else 0
+    ds = delta[dim - 1]
+    return 'a.template ld<{}, {}, {}, {}>()'.format(slots[ref.name], dx, dy, ds)
+
+  printer = _FunctorPrinter(ref_printer,
+                            min_name='soda_gen::soda_min',
+                            max_name='soda_gen::soda_max')
+  ctype = stmt.haoda_type.c_type
+  lines = [
+      '// {}'.format(str(stmt).replace('\n', '\n// ')),
+      'template <> struct Stage<{}> {{'.format(desc.index),
+      '  template <class A>',
+      '  static __device__ __forceinline__ {} eval(const A& a) {{'.format(
+          ctype),
+  ]
+  for let in stmt.let:
+    lines.append('    const {} {} = {}({});'.format(let.haoda_type.c_type,
+                                                   let.name,
+                                                   let.haoda_type.c_type,
+                                                   printer(let.expr)))
+  lines.append('    return {}({});'.format(ctype, printer(stmt.expr)))
+  lines.append('  }')
+  lines.append('};')
+  return lines
+
+
+def _lcm(values: Sequence[int]) -> int:
+  result = 1
+  for v in values:
+    result = result * v // math.gcd(result, v)
+  return result
+
+
+def tuning_2d(pass_plan: planner.PassPlan, options: Dict) -> Dict[str, int]:
+  """Launch-shape constants of the 2-D template."""
+  rings = sorted({n.ring for n in pass_plan.nodes})
+  period = _lcm([r for r in rings if r <= 4]) or 1
+  chunk = options.get('chunk') or 6
+  # a chunk that is a multiple of the window depths lets the unrolled step
+  # loop rotate the register windows by renaming
+  chunk = max(period, (chunk + period - 1) // period * period)
+  chunk = min(chunk, 256)
+  return {
+      'kWarps': options.get('warps') or 4,
+      'kMinBlocks': options.get('min_blocks') or 1,
+      'kStages': options.get('stages') or 4,
+      'kChunk': chunk,
+  }
+
+
+def tuning_3d(pass_plan: planner.PassPlan, options: Dict) -> Dict[str, int]:
+  in_depth = max(
+      [1] + [n.smem_depth for n in pass_plan.nodes if n.kind == 'input'])
+  reach = 0
+  elem = 4
+  for node in pass_plan.nodes:
+    elem = max(elem, node.haoda_type.width_in_bits // 8)
+    for deltas in node.deltas:
+      for delta in deltas:
+        if delta[1] != 0:
+          reach = max(reach,
+                      abs(delta[1]) * pass_plan.strip + abs(delta[0]) +
+                      pass_plan.cells)
+  guard = (reach * elem + 127) // 128 * 128
+  return {
+      'kRows': pass_plan.rows,
+      'kMinBlocks': options.get('min_blocks') or 1,
+      'kStages': in_depth + (options.get('lookahead') or 2),
+      'kInDepth': in_depth,
+      'kGuardBytes': guard,
+  }
+
+
+def _emit_pass(ns: str, stencil, pass_plan: planner.PassPlan,
+               options: Dict) -> List[str]:
+  dim = pass_plan.dim
+  nodes = pass_plan.nodes
+  lines = ['namespace {} {{'.format(ns)]
+  lines.append('template <int N> struct NodeType;')
+  for node in nodes:
+    lines.append('template <> struct NodeType<{}> {{ using type = {}; }};  // {}'
+                 .format(node.id, node.haoda_type.c_type, node.name))
+  tuning = tuning_2d(pass_plan, options) if dim == 2 else tuning_3d(
+      pass_plan, options)
+  lines.append('struct Prog {')
+  consts = {
+      'kDim': dim,
+      'kCells': pass_plan.cells,
+      'kStrip': pass_plan.strip,
+      'kTimeBlock': pass_plan.time_block,
+      'kNumInputs': pass_plan.num_inputs,
+      'kNumOutputs': pass_plan.num_outputs,
+      'kNumNodes': len(nodes),
+      'kHaloLo0': pass_plan.halo_lo[0],
+      'kValid0': pass_plan.valid[0],
+      'kLoS': pass_plan.lo_s,
+      'kMaxLag': pass_plan.max_lag,
+  }
+  if dim == 3:
+    consts['kHaloLo1'] = pass_plan.halo_lo[1]
+    consts['kValid1'] = pass_plan.valid[1]
+  consts.update(tuning)
+  for key, value in consts.items():
+    lines.append('  static constexpr int {} = {};'.format(key, value))
+  lines.append('  template <int N> using T = typename NodeType<N>::type;')
+  lines.append('  template <int F> using StageF = soda_gen::Stage<F>;')
+  lines.append('  static constexpr soda::NodeDesc kNodes[kNumNodes] = {')
+  for node in nodes:
+    if len(node.prods) > 8:
+      raise util.SemanticError(
+          'statement %s loads more than 8 distinct tensors' % node.name)
+    prods = ', '.join(map(str, node.prods + [0] * (8 - len(node.prods))))
+    lines.append(
+        '      {{{kind}, {src}, {lag}, {ring}, {out}, {smem}, {nprod}, {{{prods}}}}},'
+        '  // {id}: {name}'.format(kind=0 if node.kind == 'input' else 1,
+                                  src=node.src,
+                                  lag=node.lag,
+                                  ring=node.ring,
+                                  out=node.out,
+                                  smem=node.smem_depth,
+                                  nprod=len(node.prods),
+                                  prods=prods,
+                                  id=node.id,
+                                  name=node.name))
+  lines.append('  };')
+  out_nodes = sorted(pass_plan.output_nodes, key=lambda n: n.out)
+  lines.append('  static constexpr int kOutputNode[kNumOutputs] = {%s};' %
+               ', '.join(str(n.id) for n in out_nodes))
+  reach_lo = [min(n.win_lo[d] for n in out_nodes) for d in range(dim)]
+  reach_hi = [max(n.win_hi[d] for n in out_nodes) for d in range(dim)]
+  lines.append('  static constexpr int kReachLo[%d] = {%s};' %
+               (dim, ', '.join(map(str, reach_lo))))
+  lines.append('  static constexpr int kReachHi[%d] = {%s};' %
+               (dim, ', '.join(map(str, reach_hi))))
+  lines.append('};')
+  lines.append('}  // namespace %s' % ns)
+  return lines
+
+
+def _c_string(text: str) -> str:
+  return '\n'.join('    "%s\\n"' % line.replace('\\', '\\\\').replace('"', '\\"')
+                   for line in text.split('\n'))
+
+
+def emit_program(stencil,
+                 time_block: Optional[int] = None,
+                 options: Optional[Dict] = None) -> str:
+  """Returns the text of the generated .cu file for ``stencil``."""
+  options = dict(options or {})
+  dim = stencil.dim
+  time_block = planner.choose_time_block(stencil, time_block)
+  schedule = planner.pass_schedule(stencil.iterate, time_block)
+  variants = sorted(set(schedule), reverse=True)
+  plans = {
+      tb: planner.make_pass_plan(stencil,
+                                 time_block=tb,
+                                 cells=options.get('cells'),
+                                 rows=options.get('rows') or 8)
+      for tb in variants
+  }
+  stages = plans[variants[0]].stages
+
+  lines = [
+      '// Generated by soda_b200.codegen.cuda from the SODA program below.',
+      '// Only functors and constexpr plan tables are generated; the kernels are',
+      '// the hand-written templates in soda_stream.cuh.',
+      '/*',
+      str(stencil),
+      '*/',
+      '#include <math.h>',
+      '#include "soda_stream.cuh"',
+      _HELPERS,
+      'namespace soda_gen {',
+      'template <int F> struct Stage;',
+  ]
+  for desc in stages:
+    lines.extend(_functor(desc, dim))
+  lines.append('}  // namespace soda_gen')
+  lines.append('')
+  lines.append('namespace soda_gen {')
+  for tb in variants:
+    lines.extend(_emit_pass('tb%d' % tb, stencil, plans[tb], options))
+  lines.append('}  // namespace soda_gen')
+  lines.append('')
+
+  # ---- host side -----------------------------------------------------------
+  lines.append('#include "soda_runtime.cuh"')
+  lines.append('')
+  lines.append('static const soda::rt::ProgramDesc& soda_program() {')
+  lines.append('  static const soda::rt::PassImpl impls[] = {')
+  for tb in variants:
+    lines.append('      soda::rt::make_pass_impl<soda_gen::tb%d::Prog>(),' % tb)
+  lines.append('  };')
+  lines.append('  static const int schedule[] = {%s};' %
+               ', '.join(str(variants.index(tb)) for tb in schedule))
+  lines.append('  static const soda::rt::ProgramDesc desc = [] {')
+  lines.append('    soda::rt::ProgramDesc d;')
+  lines.append('    memset(&d, 0, sizeof(d));')
+  lines.append('    d.info.app_name = "%s";' % stencil.app_name)
+  lines.append('    d.info.soda_source =\n%s;' % _c_string(str(stencil)))
+  lines.append('    d.info.dim = %d;' % dim)
+  lines.append('    d.info.iterate = %d;' % stencil.iterate)
+  lines.append('    d.info.num_inputs = %d;' % len(stencil.input_stmts))
+  lines.append('    d.info.num_outputs = %d;' % len(stencil.output_stmts))
+  bytes_per_cell = 0
+  for i, stmt in enumerate(stencil.input_stmts):
+    lines.append('    d.info.input_names[%d] = "%s";' % (i, stmt.name))
+    lines.append('    d.info.input_dtypes[%d] = %s;' %
+                 (i, DTYPE_CODES[str(stmt.haoda_type)]))
+    lines.append('    d.in_elem_bytes[%d] = %d;' %
+                 (i, stmt.haoda_type.width_in_bits // 8))
+    bytes_per_cell += stmt.haoda_type.width_in_bits // 8
+  for o, stmt in enumerate(stencil.output_stmts):
+    lines.append('    d.info.output_names[%d] = "%s";' % (o, stmt.name))
+    lines.append('    d.info.output_dtypes[%d] = %s;' %
+                 (o, DTYPE_CODES[str(stmt.haoda_type)]))
+    lines.append('    d.out_elem_bytes[%d] = %d;' %
+                 (o, stmt.haoda_type.width_in_bits // 8))
+    bytes_per_cell += stmt.haoda_type.width_in_bits // 8
+    lo, hi = stencil.window_bounds[stmt.name]
+    for d in range(dim):
+      lines.append('    d.info.final_lo[%d][%d] = %d;' % (o, d, max(0, -lo[d])))
+      lines.append('    d.info.final_hi[%d][%d] = %d;' % (o, d, max(0, hi[d])))
+  lines.append('    d.info.num_passes = %d;' % len(schedule))
+  lines.append('    d.info.strict_fp = %d;' %
+               (0 if options.get('fast_fp') else 1))
+  lines.append('    d.info.algorithmic_bytes_per_cell_per_pass = %d;' %
+               bytes_per_cell)
+  lines.append('    d.impls = impls;')
+  lines.append('    d.num_impls = %d;' % len(variants))
+  lines.append('    d.schedule = schedule;')
+  lines.append('    return d;')
+  lines.append('  }();')
+  lines.append('  return desc;')
+  lines.append('}')
+  lines.append('')
+
+  # program-named entry point mirroring soda::app::<app>
+  params = []
+  for stmt in stencil.input_stmts:
+    params.append('const %s* var_%s_ptr' % (stmt.haoda_type.c_type, stmt.name))
+    params.extend('const int32_t* var_%s_%s' % (stmt.name, what)
+                  for what in ('extent', 'stride', 'min'))
+  for stmt in stencil.output_stmts:
+    params.append('%s* var_%s_ptr' % (stmt.haoda_type.c_type, stmt.name))
+    params.extend('const int32_t* var_%s_%s' % (stmt.name, what)
+                  for what in ('extent', 'stride', 'min'))
+  params.append('const soda_cuda_opts* opts')
+  lines.append('// reference: soda::app::%s (src/soda/codegen/frt/host.py:62-89)' %
+               stencil.app_name)
+  lines.append('extern "C" int soda_cuda_%s(\n    %s) {' %
+               (stencil.app_name, ',\n    '.join(params)))
+  first = stencil.input_stmts[0].name
+  for stmt in stencil.input_stmts + stencil.output_stmts:
+    for what in ('min',):
+      lines.append('  (void)var_%s_%s;' % (stmt.name, what))
+  lines.append('  if (var_%s_extent == nullptr)' % first)
+  lines.append('    return soda::rt::fail(SODA_CUDA_BAD_ARGUMENT, '
+               '"extent is NULL");')
+  for stmt in stencil.input_stmts[1:] + stencil.output_stmts:
+    lines.append('  if (var_%s_extent != nullptr)' % stmt.name)
+    lines.append('    for (int d = 0; d < %d; ++d)' % dim)
+    lines.append('      if (var_%s_extent[d] != var_%s_extent[d])' %
+                 (stmt.name, first))
+    lines.append('        return soda::rt::fail(SODA_CUDA_BAD_ARGUMENT, '
+                 '"all tensors must share one extent");')
+  lines.append('  const void* in_ptrs[] = {%s};' %
+               ', '.join('var_%s_ptr' % s.name for s in stencil.input_stmts))
+  lines.append('  const int32_t* in_strides[] = {%s};' %
+               ', '.join('var_%s_stride' % s.name for s in stencil.input_stmts))
+  lines.append('  void* out_ptrs[] = {%s};' %
+               ', '.join('var_%s_ptr' % s.name for s in stencil.output_stmts))
+  lines.append('  const int32_t* out_strides[] = {%s};' % ', '.join(
+      'var_%s_stride' % s.name for s in stencil.output_stmts))
+  lines.append('  return soda_cuda_run_host(in_ptrs, in_strides, out_ptrs, '
+               'out_strides, var_%s_extent, opts);' % first)
+  lines.append('}')
+  return '\n'.join(lines) + '\n'

@@ -1,0 +1,324 @@
+"""Tiling / temporal-blocking planner over the stencil IR.
+
+Turns one ``Stencil`` into a *pass plan*: the DAG of one HBM round trip, i.e.
+``time_block`` consecutive iterations of the program's statements fused into
+one kernel, together with everything the hand-written kernel templates need as
+compile-time tables:
+
+* ``lag``      - node ``n`` produces slice ``t - lag[n]`` of the streamed (last)
+                 dimension at step ``t`` (the step at which input slice ``t``
+                 arrives).  This is the closed form of the produce offsets that
+                 the reference obtains from an ILP over stream offsets
+                 (reference: src/soda/core.py:371-446).
+* ``ring``     - how many slices of a node each thread keeps in its register
+                 sliding window; the GPU counterpart of the reference's reuse
+                 buffers, whose length is the reuse distance
+                 (reference: src/soda/core.py:505-552,684-795).
+* halos        - how far validity shrinks in the non-streamed dimensions after
+                 the whole pass, which fixes the overlap between neighbouring
+                 tiles (the reference's host tiling uses the stencil window the
+                 same way, reference: src/soda/codegen/frt/host.py:124-131).
+
+Streaming layout: threads of a warp own ``cells`` adjacent dimension-0 cells
+each (so a warp covers ``32 * cells`` contiguous cells); the last dimension is
+streamed slice by slice.  In 2-D every warp is an independent strip; in 3-D the
+warps of a CTA are the rows (dimension 1) of a tile and exchange dimension-1
+neighbours through shared-memory planes.
+"""
+import dataclasses
+from typing import Dict, List, Optional, Sequence, Tuple
+
+from soda_b200 import ir, util, visitor
+
+WARP = 32
+
+
+@dataclasses.dataclass
+class Node:
+  id: int
+  kind: str  # 'input' | 'stage'
+  src: int  # input index, or statement index within one iteration
+  iteration: int
+  name: str
+  haoda_type: ir.Type
+  prods: List[int] = dataclasses.field(default_factory=list)  # by slot K
+  deltas: List[List[Tuple[int, ...]]] = dataclasses.field(
+      default_factory=list)  # by slot K
+  lag: int = 0
+  ring: int = 1
+  out: int = -1  # index of the output array this node is stored to, or -1
+  # cells of the strip/tile that are invalid at the low / high end, per
+  # non-streamed dimension
+  halo_lo: Tuple[int, ...] = ()
+  halo_hi: Tuple[int, ...] = ()
+  # bounds of the dependency cone towards the pass inputs, per dimension
+  win_lo: Tuple[int, ...] = ()
+  win_hi: Tuple[int, ...] = ()
+  # 3-D only: planes kept in shared memory for dimension-1 neighbours
+  smem_depth: int = 0
+
+
+@dataclasses.dataclass
+class StageDesc:
+  """One statement of the program (shared by all iterations of a pass)."""
+  index: int
+  stmt: object
+  slots: List[str]  # distinct loaded tensor names, slot order
+
+
+@dataclasses.dataclass
+class PassPlan:
+  dim: int
+  time_block: int
+  cells: int  # cells per lane (C)
+  strip: int  # cells per warp in dimension 0 (32 * C)
+  nodes: List[Node]
+  stages: List[StageDesc]
+  num_inputs: int
+  num_outputs: int
+  halo_lo: Tuple[int, ...]  # aligned halos of the pass outputs
+  halo_hi: Tuple[int, ...]
+  valid: Tuple[int, ...]  # valid cells per non-streamed dim per strip/tile
+  lo_s: int  # lowest input slice (relative) an output slice depends on
+  max_lag: int
+  rows: int = 1  # 3-D: tile rows (= warps per CTA)
+
+  @property
+  def output_nodes(self) -> List[Node]:
+    return [n for n in self.nodes if n.out >= 0]
+
+
+def stage_descs(stencil) -> List[StageDesc]:
+  """Statements of one iteration in dependency order with their load slots."""
+  stmts = list(stencil.local_stmts) + list(stencil.output_stmts)
+  names = {s.name for s in stmts}
+  deps = {}
+  for s in stmts:
+    loaded = set()
+    for ref in _stmt_loads(s):
+      if ref.name in names:
+        loaded.add(ref.name)
+    deps[s.name] = loaded
+  order: List = []
+  done = set()
+  pending = list(stmts)
+  while pending:
+    progress = False
+    for s in list(pending):
+      if deps[s.name] <= done:
+        order.append(s)
+        done.add(s.name)
+        pending.remove(s)
+        progress = True
+    if not progress:
+      raise util.SemanticError('cyclic dependency among statements')
+  result = []
+  for i, s in enumerate(order):
+    slots: List[str] = []
+    for ref in _stmt_loads(s):
+      if ref.name not in slots:
+        slots.append(ref.name)
+    result.append(StageDesc(index=i, stmt=s, slots=slots))
+  return result
+
+
+def _stmt_loads(stmt) -> Tuple[ir.Ref, ...]:
+  loads: Tuple[ir.Ref, ...] = ()
+  for let in stmt.let:
+    loads += visitor.get_load_tuple(let)
+  return loads + visitor.get_load_tuple(stmt.expr)
+
+
+def _round_up(value: int, multiple: int) -> int:
+  return (value + multiple - 1) // multiple * multiple
+
+
+def default_cells(stencil) -> int:
+  """Cells per lane: 16-byte vectors for the widest element type."""
+  widest = max(t.width_in_bits for t in stencil.input_types +
+               stencil.output_types + tuple(stencil.local_types))
+  return max(2, 128 // max(widest, 32))
+
+
+def make_pass_plan(stencil,
+                   time_block: int = 1,
+                   cells: Optional[int] = None,
+                   rows: int = 8) -> PassPlan:
+  """Plans one pass of ``time_block`` fused iterations.
+
+  ``rows`` is only used by 3-D programs (tile height = warps per CTA).
+  """
+  if stencil.param_stmts:
+    raise util.SemanticError('param statements are not supported by the CUDA '
+                             'backend')
+  dim = stencil.dim
+  if dim not in (2, 3):
+    raise util.SemanticError(
+        'the CUDA backend supports 2-D and 3-D programs, got %d-D' % dim)
+  if time_block < 1:
+    raise util.SemanticError('time block must be positive')
+  if time_block > 1 and len(stencil.input_stmts) != len(stencil.output_stmts):
+    raise util.SemanticError('cannot fuse iterations of a program whose '
+                             'inputs and outputs differ in number')
+  for t in stencil.input_types + stencil.output_types + tuple(
+      stencil.local_types):
+    if not t.is_executable:
+      raise util.SemanticError('type %s is not supported by the CUDA backend' %
+                               t)
+  cells = cells or default_cells(stencil)
+  strip = WARP * cells
+  stages = stage_descs(stencil)
+  num_inputs = len(stencil.input_stmts)
+  num_outputs = len(stencil.output_stmts)
+  input_names = stencil.input_names
+  output_names = stencil.output_names
+  s_dim = dim - 1
+
+  nodes: List[Node] = []
+  zero = (0,) * dim
+  for i, stmt in enumerate(stencil.input_stmts):
+    nodes.append(
+        Node(id=i,
+             kind='input',
+             src=i,
+             iteration=0,
+             name=stmt.name,
+             haoda_type=stmt.haoda_type,
+             halo_lo=(0,) * (dim - 1),
+             halo_hi=(0,) * (dim - 1),
+             win_lo=zero,
+             win_hi=zero))
+
+  # name -> node id within the current iteration
+  for iteration in range(time_block):
+    table: Dict[str, int] = {}
+    for i, name in enumerate(input_names):
+      if iteration == 0:
+        table[name] = i
+      else:
+        prev_out = output_names[i]
+        table[name] = prev_iter_table[prev_out]  # noqa: F821
+    for desc in stages:
+      stmt = desc.stmt
+      node = Node(id=len(nodes),
+                  kind='stage',
+                  src=desc.index,
+                  iteration=iteration,
+                  name=stencil.name_in_iter(stmt.name, iteration)
+                  if stencil.iterate > iteration else stmt.name,
+                  haoda_type=stmt.haoda_type)
+      by_slot: Dict[str, List[Tuple[int, ...]]] = {n: [] for n in desc.slots}
+      for ref in _stmt_loads(stmt):
+        delta = tuple(a - b for a, b in zip(ref.idx, stmt.ref.idx))
+        if delta not in by_slot[ref.name]:
+          by_slot[ref.name].append(delta)
+      for name in desc.slots:
+        node.prods.append(table[name])
+        node.deltas.append(by_slot[name])
+      if iteration == time_block - 1 and stmt.name in output_names:
+        node.out = output_names.index(stmt.name)
+      nodes.append(node)
+      table[stmt.name] = node.id
+    prev_iter_table = table  # noqa: F841
+
+  # lags, window bounds and halos along the DAG (nodes are in dependency order)
+  for node in nodes:
+    if node.kind == 'input':
+      continue
+    lag = 0
+    win_lo: List[Optional[int]] = [None] * dim
+    win_hi: List[Optional[int]] = [None] * dim
+    halo_lo = [0] * (dim - 1)
+    halo_hi = [0] * (dim - 1)
+    for prod_id, deltas in zip(node.prods, node.deltas):
+      prod = nodes[prod_id]
+      for delta in deltas:
+        skew = 0
+        if dim == 3 and delta[1] != 0 and prod.kind != 'input':
+          # dimension-1 neighbours come from shared memory written by other
+          # warps in an earlier step: read one step late, one barrier per step
+          skew = 1
+        lag = max(lag, prod.lag + max(delta[s_dim], 0) + skew,
+                  prod.lag + delta[s_dim] + skew)
+        for d in range(dim):
+          lo, hi = prod.win_lo[d] + delta[d], prod.win_hi[d] + delta[d]
+          win_lo[d] = lo if win_lo[d] is None else min(win_lo[d], lo)
+          win_hi[d] = hi if win_hi[d] is None else max(win_hi[d], hi)
+        for d in range(dim - 1):
+          halo_lo[d] = max(halo_lo[d], prod.halo_lo[d] - delta[d])
+          halo_hi[d] = max(halo_hi[d], prod.halo_hi[d] + delta[d])
+    node.lag = lag
+    node.win_lo = tuple(0 if v is None else v for v in win_lo)
+    node.win_hi = tuple(0 if v is None else v for v in win_hi)
+    node.halo_lo = tuple(halo_lo)
+    node.halo_hi = tuple(halo_hi)
+
+  # register rings and shared-memory plane depths
+  for node in nodes:
+    ring = 1
+    smem_depth = 0
+    for consumer in nodes:
+      for prod_id, deltas in zip(consumer.prods, consumer.deltas):
+        if prod_id != node.id:
+          continue
+        for delta in deltas:
+          distance = consumer.lag - node.lag - delta[s_dim]
+          if distance < 0:
+            raise util.InternalError('negative reuse distance')
+          if dim == 3 and delta[1] != 0:
+            smem_depth = max(smem_depth, distance + 1)
+          else:
+            ring = max(ring, distance + 1)
+    node.ring = ring
+    node.smem_depth = smem_depth
+
+  outs = [n for n in nodes if n.out >= 0]
+  halo_lo = [max(n.halo_lo[d] for n in outs) for d in range(dim - 1)]
+  halo_hi = [max(n.halo_hi[d] for n in outs) for d in range(dim - 1)]
+  # dimension 0: keep strip origins and valid widths multiples of the vector
+  halo_lo[0] = _round_up(halo_lo[0], cells)
+  valid0 = (strip - halo_lo[0] - halo_hi[0]) // cells * cells
+  if valid0 <= 0:
+    raise util.SemanticError(
+        'stencil window (%d cells in dimension 0 after %d fused iterations) '
+        'does not fit a %d-cell strip; lower the time block' %
+        (halo_lo[0] + halo_hi[0], time_block, strip))
+  valid = [valid0]
+  if dim == 3:
+    valid1 = rows - halo_lo[1] - halo_hi[1]
+    if valid1 <= 0:
+      raise util.SemanticError(
+          'stencil window does not fit a %d-row tile; lower the time block or '
+          'raise the tile rows' % rows)
+    valid.append(valid1)
+
+  return PassPlan(dim=dim,
+                  time_block=time_block,
+                  cells=cells,
+                  strip=strip,
+                  nodes=nodes,
+                  stages=stages,
+                  num_inputs=num_inputs,
+                  num_outputs=num_outputs,
+                  halo_lo=tuple(halo_lo),
+                  halo_hi=tuple(halo_hi),
+                  valid=tuple(valid),
+                  lo_s=min(n.win_lo[s_dim] for n in outs),
+                  max_lag=max(n.lag for n in outs),
+                  rows=rows if dim == 3 else 1)
+
+
+def choose_time_block(stencil, requested: Optional[int] = None) -> int:
+  """Default temporal blocking: fuse up to 4 iterations for chain programs."""
+  if stencil.iterate == 1 or len(stencil.input_stmts) != len(
+      stencil.output_stmts):
+    return 1
+  if requested:
+    return max(1, min(requested, stencil.iterate))
+  return min(stencil.iterate, 4 if stencil.dim == 2 else 2)
+
+
+def pass_schedule(iterate: int, time_block: int) -> List[int]:
+  """Iterations fused by each successive pass, e.g. 10 by 4 -> [4, 4, 2]."""
+  full, rest = divmod(iterate, time_block)
+  return [time_block] * full + ([rest] if rest else [])

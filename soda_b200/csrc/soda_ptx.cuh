@@ -1,0 +1,131 @@
+// sm_100a primitives used by the SODA stencil templates: mbarrier, TMA tiled
+// loads (cp.async.bulk.tensor), warp shuffles and vector global stores.
+// Everything here is a thin inline-PTX wrapper; no algorithm lives in this file.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace soda {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ unsigned char* dyn_smem() {
+  extern __shared__ __align__(1024) unsigned char soda_dyn_smem[];
+  return soda_dyn_smem;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(ptr));
+}
+
+// ---- mbarrier -----------------------------------------------------------
+struct alignas(8) Mbarrier {
+  uint64_t state;
+};
+
+__device__ __forceinline__ void mbar_init(Mbarrier* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(count)
+               : "memory");
+}
+
+// makes mbarrier.init visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// orders prior generic-proxy accesses to shared memory before later
+// async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(Mbarrier* bar,
+                                                      uint32_t bytes) {
+  asm volatile(
+      "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "r"(bytes)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(Mbarrier* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SODA_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SODA_MBAR_DONE;\n"
+      "bra SODA_MBAR_WAIT;\n"
+      "SODA_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---- TMA ----------------------------------------------------------------
+using TensorMap = CUtensorMap;
+
+__device__ __forceinline__ void tma_prefetch_desc(const TensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(
+                   reinterpret_cast<uint64_t>(map))
+               : "memory");
+}
+
+// Loads the box whose low corner is (c0, c1) into shared memory; out-of-range
+// elements are zero-filled by the hardware.  Completion is signalled on `bar`.
+__device__ __forceinline__ void tma_load_2d(void* dst, const TensorMap* map,
+                                            int c0, int c1, Mbarrier* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::"
+      "complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1),
+      "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const TensorMap* map,
+                                            int c0, int c1, int c2,
+                                            Mbarrier* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::"
+      "complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- warp shuffles ---------------------------------------------------------
+// Value of `v` held by the lane `delta` positions to the right (delta > 0) or
+// left (delta < 0).  Lanes whose source falls outside the warp get their own
+// value back; the templates only ever store cells for which that cannot
+// happen.
+template <int kDelta, typename T>
+__device__ __forceinline__ T shfl_rel(T v) {
+  static_assert(kDelta != 0 && kDelta > -32 && kDelta < 32, "bad lane delta");
+  if constexpr (sizeof(T) < 4) {
+    int w = static_cast<int>(v);
+    w = kDelta > 0 ? __shfl_down_sync(kFullMask, w, kDelta)
+                   : __shfl_up_sync(kFullMask, w, -kDelta);
+    return static_cast<T>(w);
+  } else {
+    return kDelta > 0 ? __shfl_down_sync(kFullMask, v, kDelta)
+                      : __shfl_up_sync(kFullMask, v, -kDelta);
+  }
+}
+
+__device__ __forceinline__ void warp_sync() { __syncwarp(); }
+__device__ __forceinline__ void cta_sync() { __syncthreads(); }
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+}  // namespace soda
+
+#include "soda_vec.cuh"
+
+// kernel launch (a macro so that the CPU emulation used by the tests can
+// substitute its own launcher for the <<<>>> syntax)
+#define SODA_LAUNCH(kernel, grid, threads, smem_bytes, stream, params) \
+  kernel<<<grid, threads, smem_bytes, stream>>>(params)

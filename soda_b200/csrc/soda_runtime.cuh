@@ -1,0 +1,748 @@
+// Host side of a compiled SODA program: implements the C ABI declared in
+// include/soda_cuda.h on top of the kernel templates in soda_stream.cuh.
+//
+// Included at the end of every generated program file, after the generated
+// code has defined
+//     static const soda::rt::ProgramDesc& soda_program();
+// Nothing here depends on the program; everything program-specific arrives
+// through ProgramDesc (metadata) and PassImpl::launch (instantiated template).
+#pragma once
+
+#ifndef SODA_EMU
+#include <cuda.h>
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "soda_cuda.h"
+#include "soda_stream.cuh"
+
+namespace soda {
+namespace rt {
+
+constexpr int kMaxT = SODA_CUDA_MAX_TENSORS;
+constexpr int kMaxD = SODA_CUDA_MAX_DIM;
+constexpr int kNumSms = 148;  // B200
+
+// ---- errors -----------------------------------------------------------------
+inline std::string& last_error() {
+  static thread_local std::string message;
+  return message;
+}
+
+inline int fail(int status, const std::string& message) {
+  last_error() = message;
+  return status;
+}
+
+#define SODA_CUDA_CHECK(expr)                                              \
+  do {                                                                     \
+    cudaError_t soda_err_ = (expr);                                        \
+    if (soda_err_ != cudaSuccess) {                                        \
+      return ::soda::rt::fail(                                             \
+          soda_err_ == cudaErrorMemoryAllocation ? SODA_CUDA_OUT_OF_MEMORY \
+                                                 : SODA_CUDA_CUDA_ERROR,   \
+          std::string(#expr) + ": " + cudaGetErrorString(soda_err_));      \
+    }                                                                      \
+  } while (0)
+
+inline std::atomic<long long>& launch_counter() {
+  static std::atomic<long long> counter{0};
+  return counter;
+}
+
+// ---- one pass ---------------------------------------------------------------
+struct PassArgs {
+  int extent[kMaxD];
+  const void* in[kMaxT];
+  long long in_pitch[kMaxT][2];  // elements: between rows, between planes
+  void* out[kMaxT];
+  long long out_pitch[kMaxT][2];
+  int box_lo[kMaxT][kMaxD];  // cells each output may be written in
+  int box_hi[kMaxT][kMaxD];
+  int segment;  // output slices per CTA along the streamed dim, 0 = auto
+  cudaStream_t stream;
+};
+
+struct PassImpl {
+  soda_cuda_pass_info info;
+  int (*launch)(const PassArgs&);
+};
+
+struct ProgramDesc {
+  soda_cuda_program_info info;
+  int in_elem_bytes[kMaxT];
+  int out_elem_bytes[kMaxT];
+  const PassImpl* impls;
+  int num_impls;
+  const int* schedule;  // impl index of every pass
+};
+
+// ---- TMA descriptors ----------------------------------------------------------
+template <typename T>
+constexpr CUtensorMapDataType tma_dtype() {
+  if (std::is_same<T, float>::value) return CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  if (std::is_same<T, double>::value) return CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+  if (sizeof(T) == 1) return CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  if (sizeof(T) == 2) return CU_TENSOR_MAP_DATA_TYPE_UINT16;
+  if (sizeof(T) == 4)
+    return std::is_signed<T>::value ? CU_TENSOR_MAP_DATA_TYPE_INT32
+                                    : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+  return std::is_signed<T>::value ? CU_TENSOR_MAP_DATA_TYPE_INT64
+                                  : CU_TENSOR_MAP_DATA_TYPE_UINT64;
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
+                                   void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult query;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault,
+                                &query) != cudaSuccess ||
+        query != cudaDriverEntryPointSuccess) {
+      ptr = nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+
+// Tiled map over a dense-in-dim-0 tensor: extent[d] cells, pitch[d-1] elements
+// between indices of dimension d; box[d] cells per load.  Out-of-range cells
+// read as zero.
+template <typename T>
+int make_tensor_map(CUtensorMap* map, const void* base, int rank,
+                    const int* extent, const long long* pitch,
+                    const int* box) {
+  EncodeTiledFn encode = encode_tiled_fn();
+  if (encode == nullptr)
+    return fail(SODA_CUDA_CUDA_ERROR,
+                "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[kMaxD];
+  cuuint64_t strides[kMaxD];
+  cuuint32_t box_dims[kMaxD];
+  cuuint32_t elem_strides[kMaxD];
+  for (int d = 0; d < rank; ++d) {
+    dims[d] = static_cast<cuuint64_t>(extent[d]);
+    box_dims[d] = static_cast<cuuint32_t>(box[d]);
+    elem_strides[d] = 1;
+    if (d > 0) strides[d - 1] = static_cast<cuuint64_t>(pitch[d - 1]) * sizeof(T);
+  }
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0)
+    return fail(SODA_CUDA_BAD_ARGUMENT,
+                "device arrays must be 16-byte aligned for TMA");
+  for (int d = 0; d + 1 < rank; ++d) {
+    if (strides[d] % 16 != 0)
+      return fail(SODA_CUDA_BAD_ARGUMENT,
+                  "device array pitches must be multiples of 16 bytes for TMA");
+  }
+  CUresult res = encode(map, tma_dtype<T>(), static_cast<cuuint32_t>(rank),
+                        const_cast<void*>(base), dims, strides, box_dims,
+                        elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (res != CUDA_SUCCESS)
+    return fail(SODA_CUDA_CUDA_ERROR, "cuTensorMapEncodeTiled failed with code " +
+                                          std::to_string(static_cast<int>(res)));
+  return SODA_CUDA_OK;
+}
+
+template <class Prog, int M = 0>
+int make_input_maps(CUtensorMap* maps, const PassArgs& a, const int* box) {
+  if constexpr (M < Prog::kNumInputs) {
+    using T = typename Prog::template T<M>;
+    int status = make_tensor_map<T>(&maps[M], a.in[M], Prog::kDim, a.extent,
+                                    a.in_pitch[M], box);
+    if (status != SODA_CUDA_OK) return status;
+    return make_input_maps<Prog, M + 1>(maps, a, box);
+  } else {
+    return SODA_CUDA_OK;
+  }
+}
+
+template <class Prog, int O = 0>
+bool outputs_vector_aligned(const PassArgs& a) {
+  if constexpr (O < Prog::kNumOutputs) {
+    constexpr int kNode = Prog::kOutputNode[O];
+    using T = typename Prog::template T<kNode>;
+    constexpr size_t kVec =
+        sizeof(T) * Prog::kCells >= 16 ? 16 : sizeof(T) * Prog::kCells;
+    bool ok = reinterpret_cast<uintptr_t>(a.out[O]) % kVec == 0 &&
+              (a.out_pitch[O][0] * sizeof(T)) % kVec == 0 &&
+              (Prog::kDim < 3 || (a.out_pitch[O][1] * sizeof(T)) % kVec == 0);
+    return ok && outputs_vector_aligned<Prog, O + 1>(a);
+  } else {
+    return true;
+  }
+}
+
+inline int floor_to(int value, int multiple) {
+  int q = value / multiple;
+  if (value % multiple != 0 && value < 0) --q;
+  return q * multiple;
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Segments along the streamed dimension: enough CTAs for several waves, but
+// long enough that the warm-up slices (the pass's reach) stay a small fraction.
+inline int choose_segment(int slices, int ctas_per_slice_set, int warmup,
+                          int ctas_per_sm, int requested) {
+  if (requested > 0) return requested < slices ? requested : slices;
+  const int min_segment = warmup * 16 > 64 ? warmup * 16 : 64;
+  const long long target_ctas = 4LL * kNumSms * ctas_per_sm;
+  long long segments = target_ctas / (ctas_per_slice_set > 0 ? ctas_per_slice_set : 1);
+  if (segments < 1) segments = 1;
+  long long max_segments = slices / min_segment;
+  if (max_segments < 1) max_segments = 1;
+  if (segments > max_segments) segments = max_segments;
+  return ceil_div(slices, static_cast<int>(segments));
+}
+
+template <class Prog>
+int launch_pass_2d(const PassArgs& a) {
+  using S = Smem2D<Prog>;
+  auto kernel = soda_stream2d_kernel<Prog>;
+  static std::once_flag once;
+  static cudaError_t attr_status = cudaSuccess;
+  static int ctas_per_sm = 1;
+  std::call_once(once, [&] {
+    attr_status = cudaFuncSetAttribute(
+        kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes);
+    if (attr_status == cudaSuccess)
+      attr_status = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &ctas_per_sm, kernel, Prog::kWarps * 32, S::kBytes);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  });
+  SODA_CUDA_CHECK(attr_status);
+
+  Params2D<Prog> p;
+  memset(&p, 0, sizeof(p));
+  const int box[2] = {Prog::kStrip, Prog::kChunk};
+  int status = make_input_maps<Prog>(p.in_map, a, box);
+  if (status != SODA_CUDA_OK) return status;
+
+  int x_lo = a.extent[0], x_hi = 0, row_lo = a.extent[1], row_hi = 0;
+  for (int o = 0; o < Prog::kNumOutputs; ++o) {
+    p.out[o] = a.out[o];
+    p.out_pitch[o] = a.out_pitch[o][0];
+    for (int d = 0; d < 2; ++d) {
+      p.box_lo[o][d] = a.box_lo[o][d];
+      p.box_hi[o][d] = a.box_hi[o][d];
+    }
+    if (a.box_lo[o][0] < x_lo) x_lo = a.box_lo[o][0];
+    if (a.box_hi[o][0] > x_hi) x_hi = a.box_hi[o][0];
+    if (a.box_lo[o][1] < row_lo) row_lo = a.box_lo[o][1];
+    if (a.box_hi[o][1] > row_hi) row_hi = a.box_hi[o][1];
+  }
+  if (x_hi <= x_lo || row_hi <= row_lo) return SODA_CUDA_OK;  // nothing valid
+
+  p.x_origin = floor_to(x_lo, Prog::kCells);
+  p.num_strips = ceil_div(x_hi - p.x_origin, Prog::kValid0);
+  p.row_lo = row_lo;
+  p.row_hi = row_hi;
+  const int ctas_x = ceil_div(p.num_strips, Prog::kWarps);
+  p.seg_rows = choose_segment(row_hi - row_lo, ctas_x,
+                              Prog::kMaxLag - Prog::kLoS, ctas_per_sm, a.segment);
+  p.vec_ok = outputs_vector_aligned<Prog>(a) ? 1 : 0;
+  dim3 grid(ctas_x, ceil_div(row_hi - row_lo, p.seg_rows), 1);
+  SODA_LAUNCH(kernel, grid, Prog::kWarps * 32, S::kBytes, a.stream, p);
+  launch_counter().fetch_add(1);
+  SODA_CUDA_CHECK(cudaGetLastError());
+  return SODA_CUDA_OK;
+}
+
+template <class Prog>
+int launch_pass_3d(const PassArgs& a) {
+  using S = Smem3D<Prog>;
+  auto kernel = soda_stream3d_kernel<Prog>;
+  static std::once_flag once;
+  static cudaError_t attr_status = cudaSuccess;
+  static int ctas_per_sm = 1;
+  std::call_once(once, [&] {
+    attr_status = cudaFuncSetAttribute(
+        kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes);
+    if (attr_status == cudaSuccess)
+      attr_status = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &ctas_per_sm, kernel, Prog::kRows * 32, S::kBytes);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  });
+  SODA_CUDA_CHECK(attr_status);
+
+  Params3D<Prog> p;
+  memset(&p, 0, sizeof(p));
+  const int box[3] = {Prog::kStrip, Prog::kRows, 1};
+  int status = make_input_maps<Prog>(p.in_map, a, box);
+  if (status != SODA_CUDA_OK) return status;
+
+  int lo[3] = {a.extent[0], a.extent[1], a.extent[2]}, hi[3] = {0, 0, 0};
+  for (int o = 0; o < Prog::kNumOutputs; ++o) {
+    p.out[o] = a.out[o];
+    p.out_pitch[o] = a.out_pitch[o][0];
+    p.out_plane_pitch[o] = a.out_pitch[o][1];
+    for (int d = 0; d < 3; ++d) {
+      p.box_lo[o][d] = a.box_lo[o][d];
+      p.box_hi[o][d] = a.box_hi[o][d];
+      if (a.box_lo[o][d] < lo[d]) lo[d] = a.box_lo[o][d];
+      if (a.box_hi[o][d] > hi[d]) hi[d] = a.box_hi[o][d];
+    }
+  }
+  for (int d = 0; d < 3; ++d)
+    if (hi[d] <= lo[d]) return SODA_CUDA_OK;
+
+  p.x_origin = floor_to(lo[0], Prog::kCells);
+  p.y_origin = lo[1];
+  p.plane_lo = lo[2];
+  p.plane_hi = hi[2];
+  const int tiles_x = ceil_div(hi[0] - p.x_origin, Prog::kValid0);
+  const int tiles_y = ceil_div(hi[1] - lo[1], Prog::kValid1);
+  p.seg_planes = choose_segment(hi[2] - lo[2], tiles_x * tiles_y,
+                                Prog::kMaxLag - Prog::kLoS, ctas_per_sm, a.segment);
+  p.vec_ok = outputs_vector_aligned<Prog>(a) ? 1 : 0;
+  dim3 grid(tiles_x, tiles_y, ceil_div(hi[2] - lo[2], p.seg_planes));
+  SODA_LAUNCH(kernel, grid, Prog::kRows * 32, S::kBytes, a.stream, p);
+  launch_counter().fetch_add(1);
+  SODA_CUDA_CHECK(cudaGetLastError());
+  return SODA_CUDA_OK;
+}
+
+template <class Prog>
+int launch_pass(const PassArgs& a) {
+  if constexpr (Prog::kDim == 2) {
+    return launch_pass_2d<Prog>(a);
+  } else {
+    return launch_pass_3d<Prog>(a);
+  }
+}
+
+template <class Prog>
+soda_cuda_pass_info pass_info_of() {
+  soda_cuda_pass_info info;
+  memset(&info, 0, sizeof(info));
+  info.time_block = Prog::kTimeBlock;
+  for (int d = 0; d < Prog::kDim; ++d) {
+    info.reach_lo[d] = Prog::kReachLo[d];
+    info.reach_hi[d] = Prog::kReachHi[d];
+  }
+  info.cells_per_lane = Prog::kCells;
+  info.strip_cells = Prog::kStrip;
+  info.valid_cells[0] = Prog::kValid0;
+  if constexpr (Prog::kDim == 2) {
+    info.threads_per_cta = Prog::kWarps * 32;
+    info.smem_bytes = Smem2D<Prog>::kBytes;
+  } else {
+    info.threads_per_cta = Prog::kRows * 32;
+    info.smem_bytes = Smem3D<Prog>::kBytes;
+    info.valid_cells[1] = Prog::kValid1;
+  }
+  return info;
+}
+
+template <class Prog>
+PassImpl make_pass_impl() {
+  PassImpl impl;
+  impl.info = pass_info_of<Prog>();
+  impl.launch = &launch_pass<Prog>;
+  return impl;
+}
+
+}  // namespace rt
+}  // namespace soda
+
+// the generated file defines this before including the runtime
+static const soda::rt::ProgramDesc& soda_program();
+
+// ---- plan ---------------------------------------------------------------------
+struct soda_cuda_plan {
+  int extent[soda::rt::kMaxD];
+  int device;
+  cudaStream_t stream;
+  int segment;
+  // device staging for host-array calls
+  void* d_in[soda::rt::kMaxT];
+  void* d_out[soda::rt::kMaxT];
+  // ping-pong scratch between passes, per output
+  void* scratch[2][soda::rt::kMaxT];
+  long long pitch[2];  // elements between rows / planes of every plan buffer
+};
+
+namespace soda {
+namespace rt {
+
+inline long long plan_cells(const soda_cuda_plan* plan, int dim) {
+  return dim == 2 ? plan->pitch[0] * plan->extent[1]
+                  : plan->pitch[1] * plan->extent[2];
+}
+
+inline int plan_alloc(soda_cuda_plan* plan, void** ptr, int elem_bytes) {
+  const ProgramDesc& prog = soda_program();
+  if (*ptr != nullptr) return SODA_CUDA_OK;
+  SODA_CUDA_CHECK(cudaMalloc(ptr, plan_cells(plan, prog.info.dim) * elem_bytes));
+  return SODA_CUDA_OK;
+}
+
+inline void default_boxes(const ProgramDesc& prog, const int* extent,
+                          bool final_pass, int (*lo)[kMaxD], int (*hi)[kMaxD]) {
+  for (int o = 0; o < prog.info.num_outputs; ++o) {
+    for (int d = 0; d < prog.info.dim; ++d) {
+      lo[o][d] = final_pass ? prog.info.final_lo[o][d] : 0;
+      hi[o][d] = extent[d] - (final_pass ? prog.info.final_hi[o][d] : 0);
+    }
+  }
+}
+
+// All passes on device buffers; intermediates ping-pong through plan scratch.
+inline int run_passes(soda_cuda_plan* plan, const void* const* d_in,
+                      const long long (*in_pitch)[2], void* const* d_out,
+                      const long long (*out_pitch)[2]) {
+  const ProgramDesc& prog = soda_program();
+  const int num_passes = prog.info.num_passes;
+  const int n_in = prog.info.num_inputs, n_out = prog.info.num_outputs;
+  for (int pass = 0; pass < num_passes; ++pass) {
+    const bool first = pass == 0, last = pass == num_passes - 1;
+    PassArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int d = 0; d < prog.info.dim; ++d) a.extent[d] = plan->extent[d];
+    a.segment = plan->segment;
+    a.stream = plan->stream;
+    for (int i = 0; i < n_in; ++i) {
+      if (first) {
+        a.in[i] = d_in[i];
+        a.in_pitch[i][0] = in_pitch[i][0];
+        a.in_pitch[i][1] = in_pitch[i][1];
+      } else {
+        a.in[i] = plan->scratch[(pass - 1) & 1][i];
+        a.in_pitch[i][0] = plan->pitch[0];
+        a.in_pitch[i][1] = plan->pitch[1];
+      }
+    }
+    for (int o = 0; o < n_out; ++o) {
+      if (last) {
+        a.out[o] = d_out[o];
+        a.out_pitch[o][0] = out_pitch[o][0];
+        a.out_pitch[o][1] = out_pitch[o][1];
+      } else {
+        int status = plan_alloc(plan, &plan->scratch[pass & 1][o],
+                                prog.out_elem_bytes[o]);
+        if (status != SODA_CUDA_OK) return status;
+        a.out[o] = plan->scratch[pass & 1][o];
+        a.out_pitch[o][0] = plan->pitch[0];
+        a.out_pitch[o][1] = plan->pitch[1];
+      }
+    }
+    default_boxes(prog, plan->extent, last, a.box_lo, a.box_hi);
+    int status = prog.impls[prog.schedule[pass]].launch(a);
+    if (status != SODA_CUDA_OK) return status;
+  }
+  return SODA_CUDA_OK;
+}
+
+inline int check_strides(const int32_t* stride, const int* extent, int dim,
+                         const char* what) {
+  if (stride == nullptr) return SODA_CUDA_OK;  // dense
+  if (stride[0] != 1)
+    return fail(SODA_CUDA_UNSUPPORTED,
+                std::string(what) + ": stride[0] must be 1 (dimension 0 dense)");
+  for (int d = 1; d < dim; ++d) {
+    if (static_cast<long long>(stride[d]) <
+        static_cast<long long>(stride[d - 1]) * extent[d - 1])
+      return fail(SODA_CUDA_BAD_ARGUMENT,
+                  std::string(what) + ": strides overlap");
+  }
+  return SODA_CUDA_OK;
+}
+
+// Copies the box [lo, hi) between a strided host array and a plan buffer.
+inline int copy_box(const soda_cuda_plan* plan, int dim, void* device,
+                    void* host, const int32_t* host_stride, int elem_bytes,
+                    const int* lo, const int* hi, bool to_device) {
+  long long hs[kMaxD] = {1, plan->extent[0],
+                         static_cast<long long>(plan->extent[0]) * plan->extent[1]};
+  if (host_stride != nullptr)
+    for (int d = 0; d < dim; ++d) hs[d] = host_stride[d];
+  const size_t width = static_cast<size_t>(hi[0] - lo[0]) * elem_bytes;
+  if (dim == 2) {
+    char* d_ptr = static_cast<char*>(device) +
+                  (plan->pitch[0] * lo[1] + lo[0]) * elem_bytes;
+    char* h_ptr = static_cast<char*>(host) + (hs[1] * lo[1] + lo[0]) * elem_bytes;
+    const size_t rows = hi[1] - lo[1];
+    if (to_device) {
+      SODA_CUDA_CHECK(cudaMemcpy2DAsync(d_ptr, plan->pitch[0] * elem_bytes, h_ptr,
+                                        hs[1] * elem_bytes, width, rows,
+                                        cudaMemcpyHostToDevice, plan->stream));
+    } else {
+      SODA_CUDA_CHECK(cudaMemcpy2DAsync(h_ptr, hs[1] * elem_bytes, d_ptr,
+                                        plan->pitch[0] * elem_bytes, width, rows,
+                                        cudaMemcpyDeviceToHost, plan->stream));
+    }
+    return SODA_CUDA_OK;
+  }
+  if (hs[2] % hs[1] != 0)
+    return fail(SODA_CUDA_UNSUPPORTED,
+                "3-D host arrays need stride[2] to be a multiple of stride[1]");
+  cudaMemcpy3DParms parms;
+  memset(&parms, 0, sizeof(parms));
+  cudaPitchedPtr d_pitched = make_cudaPitchedPtr(
+      device, plan->pitch[0] * elem_bytes, plan->pitch[0] * elem_bytes,
+      plan->pitch[1] / plan->pitch[0]);
+  cudaPitchedPtr h_pitched = make_cudaPitchedPtr(
+      host, hs[1] * elem_bytes, hs[1] * elem_bytes, hs[2] / hs[1]);
+  cudaPos pos = make_cudaPos(static_cast<size_t>(lo[0]) * elem_bytes, lo[1], lo[2]);
+  parms.srcPtr = to_device ? h_pitched : d_pitched;
+  parms.dstPtr = to_device ? d_pitched : h_pitched;
+  parms.srcPos = pos;
+  parms.dstPos = pos;
+  parms.extent = make_cudaExtent(width, hi[1] - lo[1], hi[2] - lo[2]);
+  parms.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  SODA_CUDA_CHECK(cudaMemcpy3DAsync(&parms, plan->stream));
+  return SODA_CUDA_OK;
+}
+
+struct DeviceGuard {
+  int previous = -1;
+  bool switched = false;
+  int enter(int device) {
+    if (device < 0) return SODA_CUDA_OK;
+    SODA_CUDA_CHECK(cudaGetDevice(&previous));
+    if (previous != device) {
+      SODA_CUDA_CHECK(cudaSetDevice(device));
+      switched = true;
+    }
+    return SODA_CUDA_OK;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(previous);
+  }
+};
+
+}  // namespace rt
+}  // namespace soda
+
+// ---- the C ABI ----------------------------------------------------------------
+extern "C" {
+
+int soda_cuda_info(soda_cuda_program_info* info) {
+  if (info == nullptr)
+    return soda::rt::fail(SODA_CUDA_BAD_ARGUMENT, "info is NULL");
+  *info = soda_program().info;
+  return SODA_CUDA_OK;
+}
+
+int soda_cuda_get_pass_info(int32_t pass_index, soda_cuda_pass_info* info) {
+  const soda::rt::ProgramDesc& prog = soda_program();
+  if (info == nullptr || pass_index < 0 || pass_index >= prog.info.num_passes)
+    return soda::rt::fail(SODA_CUDA_BAD_ARGUMENT, "bad pass index");
+  *info = prog.impls[prog.schedule[pass_index]].info;
+  return SODA_CUDA_OK;
+}
+
+const char* soda_cuda_last_error(void) { return soda::rt::last_error().c_str(); }
+
+int64_t soda_cuda_launch_count(void) { return soda::rt::launch_counter().load(); }
+
+int soda_cuda_plan_create(const int32_t* extent, const soda_cuda_opts* opts,
+                          soda_cuda_plan** out) {
+  using namespace soda::rt;
+  const ProgramDesc& prog = soda_program();
+  if (extent == nullptr || out == nullptr)
+    return fail(SODA_CUDA_BAD_ARGUMENT, "extent / plan is NULL");
+  for (int d = 0; d < prog.info.dim; ++d)
+    if (extent[d] <= 0) return fail(SODA_CUDA_BAD_ARGUMENT, "extent must be positive");
+  int device_count = 0;
+  SODA_CUDA_CHECK(cudaGetDeviceCount(&device_count));
+  if (device_count == 0)
+    return fail(SODA_CUDA_CUDA_ERROR, "no CUDA device: this library has no CPU path");
+  soda_cuda_plan* plan = new soda_cuda_plan();
+  memset(plan, 0, sizeof(*plan));
+  for (int d = 0; d < prog.info.dim; ++d) plan->extent[d] = extent[d];
+  plan->device = -1;
+  if (opts != nullptr) {
+    plan->device = opts->device;
+    plan->stream = static_cast<cudaStream_t>(opts->stream);
+    plan->segment = opts->segment;
+  }
+  if (plan->device < 0) {
+    cudaError_t err = cudaGetDevice(&plan->device);
+    if (err != cudaSuccess) {
+      delete plan;
+      return fail(SODA_CUDA_CUDA_ERROR, cudaGetErrorString(err));
+    }
+  }
+  // rows padded to 128 bytes for the widest element so TMA strides and vector
+  // stores are aligned for every tensor of the program
+  const long long row_align = 128;
+  plan->pitch[0] = (extent[0] + row_align - 1) / row_align * row_align;
+  plan->pitch[1] = prog.info.dim == 3 ? plan->pitch[0] * extent[1] : 0;
+  *out = plan;
+  return SODA_CUDA_OK;
+}
+
+int soda_cuda_plan_destroy(soda_cuda_plan* plan) {
+  using namespace soda::rt;
+  if (plan == nullptr) return SODA_CUDA_OK;
+  DeviceGuard guard;
+  guard.enter(plan->device);
+  for (int i = 0; i < kMaxT; ++i) {
+    if (plan->d_in[i]) cudaFree(plan->d_in[i]);
+    if (plan->d_out[i]) cudaFree(plan->d_out[i]);
+    if (plan->scratch[0][i]) cudaFree(plan->scratch[0][i]);
+    if (plan->scratch[1][i]) cudaFree(plan->scratch[1][i]);
+  }
+  delete plan;
+  return SODA_CUDA_OK;
+}
+
+int soda_cuda_plan_run_device(soda_cuda_plan* plan, const void* const* d_in,
+                              const int64_t (*in_pitches)[2], void* const* d_out,
+                              const int64_t (*out_pitches)[2]) {
+  using namespace soda::rt;
+  const ProgramDesc& prog = soda_program();
+  if (plan == nullptr || d_in == nullptr || d_out == nullptr ||
+      in_pitches == nullptr || out_pitches == nullptr)
+    return fail(SODA_CUDA_BAD_ARGUMENT, "NULL argument");
+  DeviceGuard guard;
+  int status = guard.enter(plan->device);
+  if (status != SODA_CUDA_OK) return status;
+  long long ip[kMaxT][2], op[kMaxT][2];
+  for (int i = 0; i < prog.info.num_inputs; ++i) {
+    if (d_in[i] == nullptr) return fail(SODA_CUDA_BAD_ARGUMENT, "NULL input");
+    ip[i][0] = in_pitches[i][0];
+    ip[i][1] = in_pitches[i][1];
+  }
+  for (int o = 0; o < prog.info.num_outputs; ++o) {
+    if (d_out[o] == nullptr) return fail(SODA_CUDA_BAD_ARGUMENT, "NULL output");
+    op[o][0] = out_pitches[o][0];
+    op[o][1] = out_pitches[o][1];
+  }
+  return run_passes(plan, d_in, ip, d_out, op);
+}
+
+int soda_cuda_plan_run_host(soda_cuda_plan* plan, const void* const* in_ptrs,
+                            const int32_t* const* in_strides,
+                            void* const* out_ptrs,
+                            const int32_t* const* out_strides) {
+  using namespace soda::rt;
+  const ProgramDesc& prog = soda_program();
+  if (plan == nullptr || in_ptrs == nullptr || out_ptrs == nullptr)
+    return fail(SODA_CUDA_BAD_ARGUMENT, "NULL argument");
+  const int dim = prog.info.dim;
+  DeviceGuard guard;
+  int status = guard.enter(plan->device);
+  if (status != SODA_CUDA_OK) return status;
+
+  const int zero[kMaxD] = {0, 0, 0};
+  long long pitches[kMaxT][2];
+  for (int i = 0; i < kMaxT; ++i) {
+    pitches[i][0] = plan->pitch[0];
+    pitches[i][1] = plan->pitch[1];
+  }
+  for (int i = 0; i < prog.info.num_inputs; ++i) {
+    if (in_ptrs[i] == nullptr) return fail(SODA_CUDA_BAD_ARGUMENT, "NULL input");
+    const int32_t* stride = in_strides ? in_strides[i] : nullptr;
+    status = check_strides(stride, plan->extent, dim, prog.info.input_names[i]);
+    if (status != SODA_CUDA_OK) return status;
+    status = plan_alloc(plan, &plan->d_in[i], prog.in_elem_bytes[i]);
+    if (status != SODA_CUDA_OK) return status;
+    status = copy_box(plan, dim, plan->d_in[i], const_cast<void*>(in_ptrs[i]),
+                      stride, prog.in_elem_bytes[i], zero, plan->extent, true);
+    if (status != SODA_CUDA_OK) return status;
+  }
+  for (int o = 0; o < prog.info.num_outputs; ++o) {
+    if (out_ptrs[o] == nullptr) return fail(SODA_CUDA_BAD_ARGUMENT, "NULL output");
+    const int32_t* stride = out_strides ? out_strides[o] : nullptr;
+    status = check_strides(stride, plan->extent, dim, prog.info.output_names[o]);
+    if (status != SODA_CUDA_OK) return status;
+    status = plan_alloc(plan, &plan->d_out[o], prog.out_elem_bytes[o]);
+    if (status != SODA_CUDA_OK) return status;
+  }
+  status = run_passes(plan, plan->d_in, pitches, plan->d_out, pitches);
+  if (status != SODA_CUDA_OK) return status;
+  // only the valid interior goes back; the rest of the caller's array is untouched
+  int lo[kMaxT][kMaxD], hi[kMaxT][kMaxD];
+  default_boxes(prog, plan->extent, true, lo, hi);
+  for (int o = 0; o < prog.info.num_outputs; ++o) {
+    bool empty = false;
+    for (int d = 0; d < dim; ++d) empty = empty || hi[o][d] <= lo[o][d];
+    if (empty) continue;
+    status = copy_box(plan, dim, plan->d_out[o], out_ptrs[o],
+                      out_strides ? out_strides[o] : nullptr,
+                      prog.out_elem_bytes[o], lo[o], hi[o], false);
+    if (status != SODA_CUDA_OK) return status;
+  }
+  SODA_CUDA_CHECK(cudaStreamSynchronize(plan->stream));
+  return SODA_CUDA_OK;
+}
+
+int soda_cuda_run_host(const void* const* in_ptrs, const int32_t* const* in_strides,
+                       void* const* out_ptrs, const int32_t* const* out_strides,
+                       const int32_t* extent, const soda_cuda_opts* opts) {
+  soda_cuda_plan* plan = nullptr;
+  int status = soda_cuda_plan_create(extent, opts, &plan);
+  if (status != SODA_CUDA_OK) return status;
+  status = soda_cuda_plan_run_host(plan, in_ptrs, in_strides, out_ptrs, out_strides);
+  soda_cuda_plan_destroy(plan);
+  return status;
+}
+
+int soda_cuda_run_pass(int32_t pass_index, const int32_t* extent,
+                       const void* const* d_in, const int64_t (*in_pitches)[2],
+                       void* const* d_out, const int64_t (*out_pitches)[2],
+                       const int32_t (*box_lo)[SODA_CUDA_MAX_DIM],
+                       const int32_t (*box_hi)[SODA_CUDA_MAX_DIM],
+                       const soda_cuda_opts* opts) {
+  using namespace soda::rt;
+  const ProgramDesc& prog = soda_program();
+  if (pass_index < 0 || pass_index >= prog.info.num_passes)
+    return fail(SODA_CUDA_BAD_ARGUMENT, "bad pass index");
+  if (extent == nullptr || d_in == nullptr || d_out == nullptr ||
+      in_pitches == nullptr || out_pitches == nullptr)
+    return fail(SODA_CUDA_BAD_ARGUMENT, "NULL argument");
+  DeviceGuard guard;
+  int status = guard.enter(opts ? opts->device : -1);
+  if (status != SODA_CUDA_OK) return status;
+  PassArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int d = 0; d < prog.info.dim; ++d) a.extent[d] = extent[d];
+  a.segment = opts ? opts->segment : 0;
+  a.stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  for (int i = 0; i < prog.info.num_inputs; ++i) {
+    a.in[i] = d_in[i];
+    a.in_pitch[i][0] = in_pitches[i][0];
+    a.in_pitch[i][1] = in_pitches[i][1];
+  }
+  for (int o = 0; o < prog.info.num_outputs; ++o) {
+    a.out[o] = d_out[o];
+    a.out_pitch[o][0] = out_pitches[o][0];
+    a.out_pitch[o][1] = out_pitches[o][1];
+  }
+  if (box_lo != nullptr && box_hi != nullptr) {
+    for (int o = 0; o < prog.info.num_outputs; ++o)
+      for (int d = 0; d < prog.info.dim; ++d) {
+        a.box_lo[o][d] = box_lo[o][d];
+        a.box_hi[o][d] = box_hi[o][d];
+      }
+  } else {
+    int ext[kMaxD] = {0, 0, 0};
+    for (int d = 0; d < prog.info.dim; ++d) ext[d] = extent[d];
+    default_boxes(prog, ext, pass_index == prog.info.num_passes - 1, a.box_lo,
+                  a.box_hi);
+  }
+  return prog.impls[prog.schedule[pass_index]].launch(a);
+}
+
+}  // extern "C"

@@ -1,0 +1,564 @@
+// Hand-written sm_100a stencil templates for SODA programs.
+//
+// A SODA program reaches these templates as a `Prog` type that carries only
+//   * one functor per statement (the expression, printed from the IR), and
+//   * constexpr plan tables (dependency DAG of one pass, lags, window sizes).
+// Tiling, TMA pipelines, sliding windows, neighbour exchange, temporal
+// blocking and stores are all written here, once.
+//
+// What the reference's FPGA micro-architecture becomes on a B200
+// (reference: src/soda/core.py:684-795, src/soda/dataflow.py:555-603,
+//  src/soda/codegen/xilinx/hls_kernel.py:665-886):
+//   reuse / line buffers      -> per-thread register sliding window over the
+//                                streamed (last) dimension: each lane keeps the
+//                                last `ring` slices of the cells it owns
+//   unrolled PEs fed by chains-> the 32 lanes of a warp own adjacent cells;
+//                                dimension-0 neighbours arrive by warp shuffle
+//   all stages + all iterate  -> every node of the pass DAG (time_block copies
+//   copies chained spatially     of every statement) is evaluated per step, in
+//                                registers, before anything returns to HBM
+//   BurstRead / BurstWrite    -> TMA tiled loads into an mbarrier ring in
+//                                shared memory; 16-byte coalesced stores
+//
+// Step t of a strip consumes input slice t; node n then produces its slice
+// t - lag[n].  Values computed from cells outside the loaded tile are garbage
+// by construction and are never stored: stores are restricted to the cells
+// whose whole dependency cone was inside the tile (plan halos) and inside the
+// grid (store box).
+#pragma once
+
+#ifdef SODA_EMU
+#include <soda_emu.h>  // CPU emulation of the primitives below (tests only)
+#else
+#include "soda_ptx.cuh"
+#endif
+
+namespace soda {
+
+constexpr int kMaxProds = 8;
+
+struct NodeDesc {
+  int kind;        // 0: pass input, 1: stage
+  int src;         // input index, or functor index
+  int lag;         // produces slice t - lag at step t
+  int ring;        // slices kept in the register window (>= 1)
+  int out;         // output array stored by this node, or -1
+  int smem_depth;  // 3-D: slices readable by other warps (0: none)
+  int nprod;
+  int prod[kMaxProds];  // producer node per functor load slot
+};
+
+__host__ __device__ constexpr int floor_div(int a, int b) {
+  return a >= 0 ? a / b : -((-a + b - 1) / b);
+}
+
+// ---- register sliding windows ------------------------------------------------
+template <class Prog, int N>
+struct RingStore : RingStore<Prog, N - 1> {
+  typename Prog::template T<N - 1> r[Prog::kNodes[N - 1].ring][Prog::kCells];
+};
+template <class Prog>
+struct RingStore<Prog, 0> {};
+
+template <class Prog>
+using Rings = RingStore<Prog, Prog::kNumNodes>;
+
+template <int N, class Prog>
+__device__ __forceinline__ auto& ring_of(Rings<Prog>& rings) {
+  return static_cast<RingStore<Prog, N + 1>&>(rings).r;
+}
+template <int N, class Prog>
+__device__ __forceinline__ const auto& ring_of(const Rings<Prog>& rings) {
+  return static_cast<const RingStore<Prog, N + 1>&>(rings).r;
+}
+
+template <class Prog, int N = 0>
+__device__ __forceinline__ void clear_rings(Rings<Prog>& rings) {
+  if constexpr (N < Prog::kNumNodes) {
+    using T = typename Prog::template T<N>;
+    auto& r = ring_of<N, Prog>(rings);
+#pragma unroll
+    for (int s = 0; s < Prog::kNodes[N].ring; ++s) {
+#pragma unroll
+      for (int i = 0; i < Prog::kCells; ++i) r[s][i] = T(0);
+    }
+    clear_rings<Prog, N + 1>(rings);
+  }
+}
+
+// Oldest slice falls out, slot ring-1 becomes free for the slice of this step.
+// With the step loop unrolled by a multiple of the ring depth the copies are
+// pure register renaming.
+template <int N, class Prog>
+__device__ __forceinline__ void advance_ring(Rings<Prog>& rings) {
+  auto& r = ring_of<N, Prog>(rings);
+#pragma unroll
+  for (int s = 0; s + 1 < Prog::kNodes[N].ring; ++s) {
+#pragma unroll
+    for (int i = 0; i < Prog::kCells; ++i) r[s][i] = r[s + 1][i];
+  }
+}
+
+// ---- accessor handed to the generated functors --------------------------------
+// ld<K, DX, DY, DS>() is the value of the K-th loaded tensor of the statement
+// at offset (DX, DY, DS) from the cell being produced (DY is always 0 in 2-D;
+// DS is the offset in the streamed dimension).
+template <class Prog, class Ctx, int N, int I>
+struct Access {
+  const Ctx& ctx;
+
+  template <int K, int DX, int DY, int DS>
+  __device__ __forceinline__ auto ld() const {
+    static_assert(K < Prog::kNodes[N].nprod, "functor loads an undeclared slot");
+    constexpr int P = Prog::kNodes[N].prod[K];
+    constexpr int kDistance = Prog::kNodes[N].lag - Prog::kNodes[P].lag - DS;
+    static_assert(kDistance >= 0, "plan: consumer runs ahead of its producer");
+    if constexpr (DY == 0) {
+      constexpr int kSlot = Prog::kNodes[P].ring - 1 - kDistance;
+      static_assert(kSlot >= 0, "plan: register window too short");
+      constexpr int kCol = I + DX;
+      constexpr int kLane = floor_div(kCol, Prog::kCells);
+      constexpr int kReg = kCol - kLane * Prog::kCells;
+      const auto v = ring_of<P, Prog>(ctx.rings)[kSlot][kReg];
+      if constexpr (kLane == 0) {
+        return v;
+      } else {
+        return shfl_rel<kLane>(v);
+      }
+    } else {
+      static_assert(Prog::kDim == 3, "dimension-1 offsets need a 3-D program");
+      static_assert(kDistance < Prog::kNodes[P].smem_depth,
+                    "plan: shared-memory window too short");
+      return ctx.template plane_load<P, kDistance, I + DX, DY>();
+    }
+  }
+};
+
+template <class Prog, class Ctx, int N, int I = 0>
+__device__ __forceinline__ void eval_cells(Ctx& ctx) {
+  if constexpr (I < Prog::kCells) {
+    using T = typename Prog::template T<N>;
+    using F = typename Prog::template StageF<Prog::kNodes[N].src>;
+    ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1][I] =
+        T(F::eval(Access<Prog, Ctx, N, I>{ctx}));
+    eval_cells<Prog, Ctx, N, I + 1>(ctx);
+  }
+}
+
+// Stores the kCells cells a lane holds for one output row segment.
+template <typename T, int kC>
+__device__ __forceinline__ void store_cells(T* dst, const T (&v)[kC], int col,
+                                            int box_lo, int box_hi,
+                                            bool vec_ok) {
+  if (vec_ok && col >= box_lo && col + kC <= box_hi) {
+    store_global_vec<T, kC>(dst, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kC; ++i) {
+      if (col + i >= box_lo && col + i < box_hi) dst[i] = v[i];
+    }
+  }
+}
+
+// =============================================================================
+// 2-D: every warp streams an independent column strip
+// =============================================================================
+
+template <class Prog>
+struct Params2D {
+  TensorMap in_map[Prog::kNumInputs];
+  void* out[Prog::kNumOutputs];
+  long long out_pitch[Prog::kNumOutputs];  // elements between rows
+  // cells [box_lo, box_hi) of each output may be written (dim 0, dim 1)
+  int box_lo[Prog::kNumOutputs][2];
+  int box_hi[Prog::kNumOutputs][2];
+  int x_origin;    // dimension-0 cell of strip 0's first valid cell
+  int num_strips;
+  int row_lo;      // first output row produced by segment 0
+  int row_hi;      // one past the last output row produced
+  int seg_rows;    // output rows per segment
+  int vec_ok;      // outputs are aligned for vector stores
+};
+
+template <class Prog>
+struct Smem2D {
+  // per warp: kStages slots, each holding kChunk rows of every input strip,
+  // laid out [input][row][cell]
+  static constexpr int kStages = Prog::kStages;
+  static constexpr int kChunk = Prog::kChunk;
+  static constexpr int kStrip = Prog::kStrip;
+
+  template <int M>
+  __host__ __device__ static constexpr int row_bytes() {
+    return int(sizeof(typename Prog::template T<M>)) * kStrip;
+  }
+  template <int M>
+  __host__ __device__ static constexpr int input_offset() {  // byte offset of input M in a slot
+    if constexpr (M == 0) {
+      return 0;
+    } else {
+      return input_offset<M - 1>() + row_bytes<M - 1>() * kChunk;
+    }
+  }
+  static constexpr int kSlotBytes = input_offset<Prog::kNumInputs>();
+  static constexpr int kWarpBytes = kSlotBytes * kStages;
+  static constexpr int kBarrierOffset = kWarpBytes * Prog::kWarps;
+  static constexpr int kBytes =
+      kBarrierOffset + int(sizeof(Mbarrier)) * kStages * Prog::kWarps;
+};
+
+template <class Prog>
+struct Ctx2D {
+  Rings<Prog> rings;
+  const Params2D<Prog>& p;
+  const unsigned char* slot_base;  // current slot of the TMA ring
+  int lane;
+  int x0;      // dimension-0 cell of the strip's first (lane 0) cell
+  int seg_lo;  // output rows [seg_lo, seg_hi) belong to this warp
+  int seg_hi;
+
+  __device__ __forceinline__ explicit Ctx2D(const Params2D<Prog>& params)
+      : p(params) {}
+};
+
+template <class Prog, class Ctx, int N>
+__device__ __forceinline__ void store_node_2d(Ctx& ctx, int t) {
+  using T = typename Prog::template T<N>;
+  constexpr int kC = Prog::kCells;
+  constexpr int kOut = Prog::kNodes[N].out;
+  const int row = t - Prog::kNodes[N].lag;
+  const int col_in_strip = ctx.lane * kC;
+  const bool lane_ok = col_in_strip >= Prog::kHaloLo0 &&
+                       col_in_strip + kC <= Prog::kHaloLo0 + Prog::kValid0;
+  const int lo = max(ctx.seg_lo, ctx.p.box_lo[kOut][1]);
+  const int hi = min(ctx.seg_hi, ctx.p.box_hi[kOut][1]);
+  if (row < lo || row >= hi || !lane_ok) return;
+  const int col = ctx.x0 + col_in_strip;
+  T* dst = static_cast<T*>(ctx.p.out[kOut]) +
+           static_cast<long long>(row) * ctx.p.out_pitch[kOut] + col;
+  store_cells<T, kC>(dst, ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1],
+                     col, ctx.p.box_lo[kOut][0], ctx.p.box_hi[kOut][0],
+                     ctx.p.vec_ok != 0);
+}
+
+// One step: every node of the pass DAG produces one row.  `r` is the row of
+// the current chunk that holds input row t.
+template <class Prog, class Ctx, int N = 0>
+__device__ __forceinline__ void step_nodes_2d(Ctx& ctx, int t, int r) {
+  if constexpr (N < Prog::kNumNodes) {
+    using T = typename Prog::template T<N>;
+    advance_ring<N, Prog>(ctx.rings);
+    if constexpr (Prog::kNodes[N].kind == 0) {
+      constexpr int M = Prog::kNodes[N].src;
+      using S = Smem2D<Prog>;
+      const T* row = reinterpret_cast<const T*>(
+          ctx.slot_base + S::template input_offset<M>() +
+          r * S::template row_bytes<M>());
+      load_shared_vec<T, Prog::kCells>(
+          ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1],
+          row + ctx.lane * Prog::kCells);
+    } else {
+      eval_cells<Prog, Ctx, N>(ctx);
+    }
+    if constexpr (Prog::kNodes[N].out >= 0) store_node_2d<Prog, Ctx, N>(ctx, t);
+    step_nodes_2d<Prog, Ctx, N + 1>(ctx, t, r);
+  }
+}
+
+template <class Prog, int M = 0>
+__device__ __forceinline__ void issue_chunk_2d(const Params2D<Prog>& p,
+                                               unsigned char* slot, int x0,
+                                               int row, Mbarrier* bar) {
+  if constexpr (M < Prog::kNumInputs) {
+    tma_load_2d(slot + Smem2D<Prog>::template input_offset<M>(), &p.in_map[M],
+                x0, row, bar);
+    issue_chunk_2d<Prog, M + 1>(p, slot, x0, row, bar);
+  }
+}
+
+template <class Prog>
+__global__ void __launch_bounds__(Prog::kWarps * 32, Prog::kMinBlocks)
+    soda_stream2d_kernel(const __grid_constant__ Params2D<Prog> p) {
+  using S = Smem2D<Prog>;
+  constexpr int kStages = S::kStages;
+  constexpr int kChunk = S::kChunk;
+  unsigned char* smem = dyn_smem();
+  const int warp = threadIdx.x >> 5;
+  const int strip = blockIdx.x * Prog::kWarps + warp;
+  if (strip >= p.num_strips) return;  // warps never meet at a CTA barrier
+
+  Ctx2D<Prog> ctx(p);
+  ctx.lane = lane_id();
+  ctx.x0 = p.x_origin + strip * Prog::kValid0 - Prog::kHaloLo0;
+  ctx.seg_lo = p.row_lo + blockIdx.y * p.seg_rows;
+  ctx.seg_hi = min(ctx.seg_lo + p.seg_rows, p.row_hi);
+  clear_rings<Prog>(ctx.rings);
+
+  unsigned char* slots = smem + warp * S::kWarpBytes;
+  Mbarrier* full =
+      reinterpret_cast<Mbarrier*>(smem + S::kBarrierOffset) + warp * kStages;
+
+  // input rows [t_begin, t_end] feed output rows [seg_lo, seg_hi)
+  const int t_begin = ctx.seg_lo + Prog::kLoS;
+  const int t_end = ctx.seg_hi - 1 + Prog::kMaxLag;
+  const int num_chunks = (t_end - t_begin + kChunk) / kChunk;
+
+  if (ctx.lane == 0) {
+#pragma unroll
+    for (int m = 0; m < Prog::kNumInputs; ++m) tma_prefetch_desc(&p.in_map[m]);
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+    for (int s = 0; s < kStages && s < num_chunks; ++s) {
+      mbar_arrive_expect_tx(&full[s], S::kSlotBytes);
+      issue_chunk_2d<Prog>(p, slots + s * S::kSlotBytes, ctx.x0,
+                           t_begin + s * kChunk, &full[s]);
+    }
+  }
+  warp_sync();
+
+  int slot = 0;
+  unsigned parity = 0;
+  for (int chunk = 0; chunk < num_chunks; ++chunk) {
+    mbar_wait(&full[slot], parity);
+    ctx.slot_base = slots + slot * S::kSlotBytes;
+    const int t0 = t_begin + chunk * kChunk;
+#pragma unroll
+    for (int r = 0; r < kChunk; ++r) step_nodes_2d<Prog>(ctx, t0 + r, r);
+    warp_sync();  // every lane is done reading the slot
+    if (ctx.lane == 0 && chunk + kStages < num_chunks) {
+      mbar_arrive_expect_tx(&full[slot], S::kSlotBytes);
+      issue_chunk_2d<Prog>(p, slots + slot * S::kSlotBytes, ctx.x0,
+                           t_begin + (chunk + kStages) * kChunk, &full[slot]);
+    }
+    if (++slot == kStages) {
+      slot = 0;
+      parity ^= 1u;
+    }
+  }
+}
+
+// =============================================================================
+// 3-D: a CTA streams a (strip x rows) tile along the last dimension; warp w owns
+// tile row w.  Dimension-0 neighbours: warp shuffles.  Dimension-1 neighbours:
+// shared-memory planes (the TMA ring for inputs, an export ring for stages),
+// read one step after they were written so that one barrier per step suffices.
+// =============================================================================
+
+template <class Prog>
+struct Params3D {
+  TensorMap in_map[Prog::kNumInputs];
+  void* out[Prog::kNumOutputs];
+  long long out_pitch[Prog::kNumOutputs];        // elements between rows
+  long long out_plane_pitch[Prog::kNumOutputs];  // elements between planes
+  int box_lo[Prog::kNumOutputs][3];
+  int box_hi[Prog::kNumOutputs][3];
+  int x_origin;   // dim-0 cell of tile column 0's first valid cell
+  int y_origin;   // dim-1 cell of tile row 0's first valid cell
+  int plane_lo;   // first output plane produced by segment 0
+  int plane_hi;
+  int seg_planes;
+  int vec_ok;
+};
+
+template <class Prog>
+struct Smem3D {
+  static constexpr int kStages = Prog::kStages;
+  static constexpr int kPlaneCells = Prog::kStrip * Prog::kRows;
+
+  template <int N>
+  __host__ __device__ static constexpr int plane_bytes() {
+    return int(sizeof(typename Prog::template T<N>)) * kPlaneCells;
+  }
+  // inputs are nodes 0 .. kNumInputs-1
+  template <int M>
+  __host__ __device__ static constexpr int input_offset() {
+    if constexpr (M == 0) {
+      return 0;
+    } else {
+      return input_offset<M - 1>() + plane_bytes<M - 1>();
+    }
+  }
+  static constexpr int kSlotBytes = input_offset<Prog::kNumInputs>();
+  static constexpr int kRingOffset = Prog::kGuardBytes;
+  static constexpr int kExportOffset = kRingOffset + kSlotBytes * kStages;
+
+  template <int N>
+  __host__ __device__ static constexpr int export_offset() {  // relative to kExportOffset
+    if constexpr (N == 0) {
+      return 0;
+    } else {
+      return export_offset<N - 1>() +
+             (Prog::kNodes[N - 1].kind == 1
+                  ? Prog::kNodes[N - 1].smem_depth * plane_bytes<N - 1>()
+                  : 0);
+    }
+  }
+  static constexpr int kExportBytes = export_offset<Prog::kNumNodes>();
+  static constexpr int kBarrierOffset =
+      (kExportOffset + kExportBytes + Prog::kGuardBytes + 127) / 128 * 128;
+  static constexpr int kBytes = kBarrierOffset + int(sizeof(Mbarrier)) * kStages;
+};
+
+template <class Prog>
+struct Ctx3D {
+  Rings<Prog> rings;
+  const Params3D<Prog>& p;
+  unsigned char* smem;
+  int lane;
+  int row;       // tile row owned by this warp
+  int cell_off;  // row * kStrip + lane * kCells
+  int step;      // steps since the start of the segment
+  int x0, y0;
+  int seg_lo, seg_hi;
+
+  __device__ __forceinline__ explicit Ctx3D(const Params3D<Prog>& params)
+      : p(params) {}
+
+  // Plane of node P produced kDistance steps before P's current one.
+  template <int P, int kDistance>
+  __device__ __forceinline__ const typename Prog::template T<P>* plane() const {
+    using S = Smem3D<Prog>;
+    using T = typename Prog::template T<P>;
+    if constexpr (Prog::kNodes[P].kind == 0) {
+      constexpr int kStages = S::kStages;
+      const int slot = (step + kStages - kDistance) % kStages;
+      return reinterpret_cast<const T*>(
+          smem + S::kRingOffset + slot * S::kSlotBytes +
+          S::template input_offset<Prog::kNodes[P].src>());
+    } else {
+      constexpr int kDepth = Prog::kNodes[P].smem_depth;
+      const int slot = (step + kDepth - kDistance) % kDepth;
+      return reinterpret_cast<const T*>(
+          smem + S::kExportOffset + S::template export_offset<P>() +
+          slot * S::template plane_bytes<P>());
+    }
+  }
+
+  template <int P, int kDistance, int kCol, int kDy>
+  __device__ __forceinline__ typename Prog::template T<P> plane_load() const {
+    return plane<P, kDistance>()[cell_off + kDy * Prog::kStrip + kCol];
+  }
+};
+
+template <class Prog, class Ctx, int N>
+__device__ __forceinline__ void store_node_3d(Ctx& ctx, int t) {
+  using T = typename Prog::template T<N>;
+  constexpr int kC = Prog::kCells;
+  constexpr int kOut = Prog::kNodes[N].out;
+  const int plane = t - Prog::kNodes[N].lag;
+  const int col_in_strip = ctx.lane * kC;
+  const bool lane_ok = col_in_strip >= Prog::kHaloLo0 &&
+                       col_in_strip + kC <= Prog::kHaloLo0 + Prog::kValid0;
+  const bool row_ok =
+      ctx.row >= Prog::kHaloLo1 && ctx.row < Prog::kHaloLo1 + Prog::kValid1;
+  const int lo = max(ctx.seg_lo, ctx.p.box_lo[kOut][2]);
+  const int hi = min(ctx.seg_hi, ctx.p.box_hi[kOut][2]);
+  const int y = ctx.y0 + ctx.row;
+  if (plane < lo || plane >= hi || !lane_ok || !row_ok ||
+      y < ctx.p.box_lo[kOut][1] || y >= ctx.p.box_hi[kOut][1])
+    return;
+  const int col = ctx.x0 + col_in_strip;
+  T* dst = static_cast<T*>(ctx.p.out[kOut]) +
+           static_cast<long long>(plane) * ctx.p.out_plane_pitch[kOut] +
+           static_cast<long long>(y) * ctx.p.out_pitch[kOut] + col;
+  store_cells<T, kC>(dst, ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1],
+                     col, ctx.p.box_lo[kOut][0], ctx.p.box_hi[kOut][0],
+                     ctx.p.vec_ok != 0);
+}
+
+template <class Prog, class Ctx, int N = 0>
+__device__ __forceinline__ void step_nodes_3d(Ctx& ctx, int t) {
+  if constexpr (N < Prog::kNumNodes) {
+    using T = typename Prog::template T<N>;
+    constexpr int kC = Prog::kCells;
+    advance_ring<N, Prog>(ctx.rings);
+    auto& newest = ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1];
+    if constexpr (Prog::kNodes[N].kind == 0) {
+      load_shared_vec<T, kC>(newest,
+                             ctx.template plane<N, 0>() + ctx.cell_off);
+    } else {
+      eval_cells<Prog, Ctx, N>(ctx);
+      if constexpr (Prog::kNodes[N].smem_depth > 0) {
+        // export for the dimension-1 neighbours (read from the next step on)
+        T* dst = const_cast<T*>(ctx.template plane<N, 0>()) + ctx.cell_off;
+        Vec<T, kC> tmp;
+#pragma unroll
+        for (int i = 0; i < kC; ++i) tmp.v[i] = newest[i];
+        *reinterpret_cast<Vec<T, kC>*>(dst) = tmp;
+      }
+    }
+    if constexpr (Prog::kNodes[N].out >= 0) store_node_3d<Prog, Ctx, N>(ctx, t);
+    step_nodes_3d<Prog, Ctx, N + 1>(ctx, t);
+  }
+}
+
+template <class Prog, int M = 0>
+__device__ __forceinline__ void issue_plane_3d(const Params3D<Prog>& p,
+                                               unsigned char* slot, int x0,
+                                               int y0, int plane,
+                                               Mbarrier* bar) {
+  if constexpr (M < Prog::kNumInputs) {
+    tma_load_3d(slot + Smem3D<Prog>::template input_offset<M>(), &p.in_map[M],
+                x0, y0, plane, bar);
+    issue_plane_3d<Prog, M + 1>(p, slot, x0, y0, plane, bar);
+  }
+}
+
+template <class Prog>
+__global__ void __launch_bounds__(Prog::kRows * 32, Prog::kMinBlocks)
+    soda_stream3d_kernel(const __grid_constant__ Params3D<Prog> p) {
+  using S = Smem3D<Prog>;
+  constexpr int kStages = S::kStages;
+  constexpr int kInDepth = Prog::kInDepth;  // input planes still readable
+  static_assert(kStages > kInDepth, "TMA ring needs look-ahead slots");
+
+  Ctx3D<Prog> ctx(p);
+  ctx.smem = dyn_smem();
+  ctx.lane = lane_id();
+  ctx.row = threadIdx.x >> 5;
+  ctx.cell_off = ctx.row * Prog::kStrip + ctx.lane * Prog::kCells;
+  ctx.x0 = p.x_origin + blockIdx.x * Prog::kValid0 - Prog::kHaloLo0;
+  ctx.y0 = p.y_origin + blockIdx.y * Prog::kValid1 - Prog::kHaloLo1;
+  ctx.seg_lo = p.plane_lo + blockIdx.z * p.seg_planes;
+  ctx.seg_hi = min(ctx.seg_lo + p.seg_planes, p.plane_hi);
+  clear_rings<Prog>(ctx.rings);
+
+  Mbarrier* full = reinterpret_cast<Mbarrier*>(ctx.smem + S::kBarrierOffset);
+  unsigned char* ring = ctx.smem + S::kRingOffset;
+  const int t_begin = ctx.seg_lo + Prog::kLoS;
+  const int num_steps = ctx.seg_hi - 1 + Prog::kMaxLag - t_begin + 1;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int m = 0; m < Prog::kNumInputs; ++m) tma_prefetch_desc(&p.in_map[m]);
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+    for (int s = 0; s < kStages && s < num_steps; ++s) {
+      mbar_arrive_expect_tx(&full[s], S::kSlotBytes);
+      issue_plane_3d<Prog>(p, ring + s * S::kSlotBytes, ctx.x0, ctx.y0,
+                           t_begin + s, &full[s]);
+    }
+  }
+  cta_sync();
+
+  int slot = 0;
+  unsigned parity = 0;
+  for (ctx.step = 0; ctx.step < num_steps; ++ctx.step) {
+    mbar_wait(&full[slot], parity);
+    step_nodes_3d<Prog>(ctx, t_begin + ctx.step);
+    cta_sync();  // exports visible; plane (step - kInDepth + 1) is dead
+    const int dead = ctx.step - (kInDepth - 1);
+    if (threadIdx.x == 0 && dead >= 0 && dead + kStages < num_steps) {
+      const int s = dead % kStages;
+      mbar_arrive_expect_tx(&full[s], S::kSlotBytes);
+      issue_plane_3d<Prog>(p, ring + s * S::kSlotBytes, ctx.x0, ctx.y0,
+                           t_begin + dead + kStages, &full[s]);
+    }
+    if (++slot == kStages) {
+      slot = 0;
+      parity ^= 1u;
+    }
+  }
+}
+
+}  // namespace soda
