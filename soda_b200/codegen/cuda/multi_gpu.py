@@ -1,0 +1,201 @@
+"""Multi-GPU slab runtime: one process per GPU, halo exchange per pass.
+
+The grid is split along the outermost (streamed, ``*``) dimension into
+contiguous slabs, one per rank - the dimension the reference itself treats as
+unbounded (reference: README.md:223, src/soda/codegen/frt/host.py:124-131 tiles
+every other dimension).  Between passes (one pass = ``time_block`` fused
+iterations) neighbouring ranks swap the ``reach`` slices next to their common
+boundary with ``torch.distributed`` point-to-point operations (NCCL send/recv
+over NVLink on GPUs, gloo in the CPU tests).  There is no other collective:
+a stencil has no reduction.
+
+Every rank's local array covers its own slices plus ``reach`` ghost slices on
+each side that exist in the global grid; at the global border there is no
+ghost, so the kernels' TMA loads zero-fill there exactly as on one GPU.  Every
+stored value therefore has the same dependency cone and the same operation
+order as in the single-GPU run: results are bit-identical.
+
+The reference has no distributed path at all; this file
+is new functionality required by BASELINE.json's north star.
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from soda_b200.codegen.cuda import launcher
+
+
+def split_slices(total: int, world: int) -> List[Tuple[int, int]]:
+  """Contiguous [begin, end) ranges of the streamed dimension per rank."""
+  base, rest = divmod(total, world)
+  ranges = []
+  begin = 0
+  for rank in range(world):
+    size = base + (1 if rank < rest else 0)
+    ranges.append((begin, begin + size))
+    begin += size
+  return ranges
+
+
+class SlabRunner:
+  """Runs a compiled program on this rank's slab of a larger global grid.
+
+  ``global_extent``: extent of the whole grid (dimension 0 first).
+  Tensors are ``torch`` tensors on ``device`` with shape
+  ``(local_slices[, extent[1]], pitch)``; ``self.inputs`` / ``self.outputs`` hold
+  the local arrays, ``self.own`` the local slice range this rank owns.
+  """
+
+  def __init__(self,
+               program: launcher.CudaProgram,
+               global_extent: Sequence[int],
+               device: torch.device,
+               rank: Optional[int] = None,
+               world: Optional[int] = None,
+               group=None,
+               stream_handle: int = 0):
+    self.program = program
+    self.group = group
+    self.rank = dist.get_rank(group) if rank is None else rank
+    self.world = dist.get_world_size(group) if world is None else world
+    self.device = device
+    self.global_extent = tuple(global_extent)
+    self.dim = program.dim
+    self.stream_handle = stream_handle
+    s_dim = self.dim - 1
+    total = self.global_extent[s_dim]
+    self.ranges = split_slices(total, self.world)
+    self.begin, self.end = self.ranges[self.rank]
+    infos = [program.pass_info(i) for i in range(program.num_passes)]
+    self.reach_lo = max(-info.reach_lo[s_dim] for info in infos)
+    self.reach_hi = max(info.reach_hi[s_dim] for info in infos)
+    self.pass_reach = [(-info.reach_lo[s_dim], info.reach_hi[s_dim])
+                       for info in infos]
+    for begin, end in self.ranges:
+      if end - begin < max(self.reach_lo, self.reach_hi):
+        raise ValueError('slab thinner than the halo: use fewer ranks')
+    # local array = owned slices + ghosts that exist globally
+    self.local_begin = max(0, self.begin - self.reach_lo)
+    self.local_end = min(total, self.end + self.reach_hi)
+    self.local_extent = self.global_extent[:s_dim] + (self.local_end -
+                                                     self.local_begin,)
+    self.own = (self.begin - self.local_begin, self.end - self.local_begin)
+    self.pitch = (self.global_extent[0] + 127) // 128 * 128
+    self.inputs = [self._alloc(dt) for dt in program.input_dtypes]
+    self.outputs = [self._alloc(dt) for dt in program.output_dtypes]
+    n = len(program.output_dtypes)
+    self.scratch = [[None] * n, [None] * n]
+    self.launches = 0
+
+  # -- buffers -------------------------------------------------------------------
+  def _torch_dtype(self, np_dtype):
+    return getattr(torch, str(np_dtype))
+
+  def _alloc(self, np_dtype) -> torch.Tensor:
+    shape = tuple(self.local_extent[1:][::-1]) + (self.pitch,)
+    return torch.zeros(shape, dtype=self._torch_dtype(np_dtype),
+                       device=self.device)
+
+  def _pitches(self):
+    plane = self.pitch * self.local_extent[1] if self.dim == 3 else 0
+    return (self.pitch, plane)
+
+  def view(self, tensor: torch.Tensor) -> torch.Tensor:
+    """The un-padded part of a local array."""
+    return tensor[..., :self.global_extent[0]]
+
+  # -- halo exchange ----------------------------------------------------------------
+  def exchange(self, tensors: Sequence[torch.Tensor], reach_lo: int,
+               reach_hi: int) -> None:
+    """Fills the ghost slices of ``tensors`` from the neighbouring ranks.
+
+    A rank's lower ghost (``reach_lo`` slices) comes from the top of the rank
+    below; its upper ghost (``reach_hi`` slices) from the bottom of the rank
+    above.
+    """
+    ops = []
+    lo, hi = self.own
+    keep = []
+    for tensor in tensors:
+      if self.rank > 0:
+        if reach_hi > 0:  # the lower neighbour's upper ghost is my bottom rows
+          send = tensor[lo:lo + reach_hi].contiguous()
+          keep.append(send)
+          ops.append(dist.P2POp(dist.isend, send, self._peer(self.rank - 1),
+                                self.group))
+        if reach_lo > 0:
+          recv = tensor[lo - reach_lo:lo]
+          ops.append(dist.P2POp(dist.irecv, recv, self._peer(self.rank - 1),
+                                self.group))
+      if self.rank < self.world - 1:
+        if reach_lo > 0:  # the upper neighbour's lower ghost is my top rows
+          send = tensor[hi - reach_lo:hi].contiguous()
+          keep.append(send)
+          ops.append(dist.P2POp(dist.isend, send, self._peer(self.rank + 1),
+                                self.group))
+        if reach_hi > 0:
+          recv = tensor[hi:hi + reach_hi]
+          ops.append(dist.P2POp(dist.irecv, recv, self._peer(self.rank + 1),
+                                self.group))
+    if ops:
+      for work in dist.batch_isend_irecv(ops):
+        work.wait()
+
+  def _peer(self, rank: int) -> int:
+    if self.group is None:
+      return rank
+    return dist.get_global_rank(self.group, rank)
+
+  # -- passes -------------------------------------------------------------------------
+  def _boxes(self, last: bool):
+    """Store boxes in local coordinates: this rank's own slices, clipped to the
+    program's final valid box on the last pass."""
+    prog = self.program
+    s_dim = self.dim - 1
+    lo_boxes, hi_boxes = [], []
+    for o in range(len(prog.output_names)):
+      lo = [0] * self.dim
+      hi = list(self.local_extent)
+      if last:
+        final = prog.valid_box(o, self.global_extent)
+        for d in range(s_dim):
+          lo[d], hi[d] = final[d]
+        g_lo = max(self.begin, final[s_dim][0])
+        g_hi = min(self.end, final[s_dim][1])
+      else:
+        g_lo, g_hi = self.begin, self.end
+      lo[s_dim] = g_lo - self.local_begin
+      hi[s_dim] = max(lo[s_dim], g_hi - self.local_begin)
+      lo_boxes.append(lo)
+      hi_boxes.append(hi)
+    return lo_boxes, hi_boxes
+
+  def run(self) -> None:
+    """All ``iterate`` iterations: ``self.inputs`` -> ``self.outputs``.  The
+    ghost slices of ``self.inputs`` are refreshed first, so callers only fill
+    the slices they own."""
+    prog = self.program
+    opts = launcher.make_opts(stream=self.stream_handle)
+    pitches = self._pitches()
+    current = self.inputs
+    for index in range(prog.num_passes):
+      last = index == prog.num_passes - 1
+      reach_lo, reach_hi = self.pass_reach[index]
+      self.exchange(current, reach_lo, reach_hi)
+      if last:
+        target = self.outputs
+      else:
+        bank = self.scratch[index & 1]
+        for o, dt in enumerate(prog.output_dtypes):
+          if bank[o] is None:
+            bank[o] = self._alloc(dt)
+        target = bank
+      box_lo, box_hi = self._boxes(last)
+      prog.run_pass(index, self.local_extent,
+                    [t.data_ptr() for t in current],
+                    [pitches] * len(current),
+                    [t.data_ptr() for t in target], [pitches] * len(target),
+                    box_lo, box_hi, opts)
+      self.launches += 1
+      current = target
