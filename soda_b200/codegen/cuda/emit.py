@@ -174,6 +174,7 @@ def _emit_pass(ns: str, stencil, pass_plan: planner.PassPlan,
       'kNumNodes': len(nodes),
       'kHaloLo0': pass_plan.halo_lo[0],
       'kValid0': pass_plan.valid[0],
+      'kAlign0': pass_plan.align0,
       'kLoS': pass_plan.lo_s,
       'kMaxLag': pass_plan.max_lag,
   }

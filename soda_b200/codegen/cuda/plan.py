@@ -82,6 +82,7 @@ class PassPlan:
   lo_s: int  # lowest input slice (relative) an output slice depends on
   max_lag: int
   rows: int = 1  # 3-D: tile rows (= warps per CTA)
+  align0: int = 1  # strip origins are multiples of this many cells
 
   @property
   def output_nodes(self) -> List[Node]:
@@ -137,7 +138,7 @@ def default_cells(stencil) -> int:
   """Cells per lane: 16-byte vectors for the widest element type."""
   widest = max(t.width_in_bits for t in stencil.input_types +
                stencil.output_types + tuple(stencil.local_types))
-  return max(2, 128 // max(widest, 32))
+  return max(2, 128 // max(widest, 16))
 
 
 def make_pass_plan(stencil,
@@ -275,9 +276,14 @@ def make_pass_plan(stencil,
   outs = [n for n in nodes if n.out >= 0]
   halo_lo = [max(n.halo_lo[d] for n in outs) for d in range(dim - 1)]
   halo_hi = [max(n.halo_hi[d] for n in outs) for d in range(dim - 1)]
-  # dimension 0: keep strip origins and valid widths multiples of the vector
-  halo_lo[0] = _round_up(halo_lo[0], cells)
-  valid0 = (strip - halo_lo[0] - halo_hi[0]) // cells * cells
+  # dimension 0: strip origins must be multiples of the lane vector (aligned
+  # vector stores) and of 16 bytes of every input (TMA faults on a box whose
+  # first element is not 16-byte aligned in global memory)
+  align0 = max([cells] + [
+      128 // t.width_in_bits for t in stencil.input_types
+  ])
+  halo_lo[0] = _round_up(halo_lo[0], align0)
+  valid0 = (strip - halo_lo[0] - halo_hi[0]) // align0 * align0
   if valid0 <= 0:
     raise util.SemanticError(
         'stencil window (%d cells in dimension 0 after %d fused iterations) '
@@ -305,7 +311,8 @@ def make_pass_plan(stencil,
                   valid=tuple(valid),
                   lo_s=min(n.win_lo[s_dim] for n in outs),
                   max_lag=max(n.lag for n in outs),
-                  rows=rows if dim == 3 else 1)
+                  rows=rows if dim == 3 else 1,
+                  align0=align0)
 
 
 def choose_time_block(stencil, requested: Optional[int] = None) -> int:

@@ -14,6 +14,7 @@
 #endif
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -121,6 +122,21 @@ inline EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+inline CUtensorMapL2promotion l2_promotion() {
+#ifndef SODA_EMU
+  const char* env = getenv("SODA_CUDA_L2_PROMOTION");
+  if (env != nullptr) {
+    switch (atoi(env)) {
+      case 0: return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+      case 64: return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+      case 128: return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+      default: break;
+    }
+  }
+#endif
+  return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
+
 // Tiled map over a dense-in-dim-0 tensor: extent[d] cells, pitch[d-1] elements
 // between indices of dimension d; box[d] cells per load.  Out-of-range cells
 // read as zero.
@@ -153,8 +169,7 @@ int make_tensor_map(CUtensorMap* map, const void* base, int rank,
   CUresult res = encode(map, tma_dtype<T>(), static_cast<cuuint32_t>(rank),
                         const_cast<void*>(base), dims, strides, box_dims,
                         elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, l2_promotion(),
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (res != CUDA_SUCCESS)
     return fail(SODA_CUDA_CUDA_ERROR, "cuTensorMapEncodeTiled failed with code " +
@@ -252,7 +267,7 @@ int launch_pass_2d(const PassArgs& a) {
   }
   if (x_hi <= x_lo || row_hi <= row_lo) return SODA_CUDA_OK;  // nothing valid
 
-  p.x_origin = floor_to(x_lo, Prog::kCells);
+  p.x_origin = floor_to(x_lo, Prog::kAlign0);
   p.num_strips = ceil_div(x_hi - p.x_origin, Prog::kValid0);
   p.row_lo = row_lo;
   p.row_hi = row_hi;
@@ -305,7 +320,7 @@ int launch_pass_3d(const PassArgs& a) {
   for (int d = 0; d < 3; ++d)
     if (hi[d] <= lo[d]) return SODA_CUDA_OK;
 
-  p.x_origin = floor_to(lo[0], Prog::kCells);
+  p.x_origin = floor_to(lo[0], Prog::kAlign0);
   p.y_origin = lo[1];
   p.plane_lo = lo[2];
   p.plane_hi = hi[2];

@@ -13,6 +13,7 @@
 #pragma once
 
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -241,6 +242,13 @@ inline void emu_tma_load(void* dst, const TensorMap* map, const int* c, Mbarrier
   for (int d = 0; d < map->rank; ++d) {
     box[d] = map->box[d];
     coord[d] = c[d];
+  }
+  // measured on B200: a box whose first element is not 16-byte aligned in
+  // global memory raises "illegal instruction"
+  if ((coord[0] * eb) % 16 != 0) {
+    fprintf(stderr, "soda_emu: TMA box start %lld x %d bytes is not 16-byte aligned\n",
+            static_cast<long long>(coord[0]), eb);
+    abort();
   }
   for (int k = 0; k < box[2]; ++k)
     for (int j = 0; j < box[1]; ++j)
