@@ -41,6 +41,14 @@
 extern "C" {
 #endif
 
+/* Program libraries are built with hidden visibility (and -fno-gnu-unique) so
+ * that several of them can live in one process; only this ABI is exported. */
+#if defined(__GNUC__)
+#define SODA_CUDA_API __attribute__((visibility("default")))
+#else
+#define SODA_CUDA_API
+#endif
+
 #define SODA_CUDA_MAX_DIM 3
 #define SODA_CUDA_MAX_TENSORS 8
 #define SODA_CUDA_MAX_PASSES 1024
@@ -106,42 +114,42 @@ typedef struct soda_cuda_plan soda_cuda_plan;   /* opaque */
 
 /* Program description.  Replaces the `// stencil window size` / kStencilDim
  * constants the reference prints into the host (src/soda/codegen/frt/host.py:686-699). */
-int soda_cuda_info(soda_cuda_program_info* info);
-int soda_cuda_get_pass_info(int32_t pass_index, soda_cuda_pass_info* info);
+SODA_CUDA_API int soda_cuda_info(soda_cuda_program_info* info);
+SODA_CUDA_API int soda_cuda_get_pass_info(int32_t pass_index, soda_cuda_pass_info* info);
 
 /* Message for the last non-zero status returned to this thread. */
-const char* soda_cuda_last_error(void);
+SODA_CUDA_API const char* soda_cuda_last_error(void);
 
 /* One-shot, host arrays in / host arrays out; host<->device copies included.
  * Generic form of soda_cuda_<app>: per-tensor arrays instead of named arguments.
  * Replaces soda::app::<app> (src/soda/codegen/frt/host.py:62-431). */
-int soda_cuda_run_host(const void* const* in_ptrs, const int32_t* const* in_strides,
+SODA_CUDA_API int soda_cuda_run_host(const void* const* in_ptrs, const int32_t* const* in_strides,
                        void* const* out_ptrs, const int32_t* const* out_strides,
                        const int32_t* extent, const soda_cuda_opts* opts);
 
 /* A plan owns the device-side scratch (ping-pong buffers, staging copies) for
  * one grid extent, like the tiled buffers the reference wrapper allocates per
  * call (src/soda/codegen/frt/host.py:149-179), but reusable across calls. */
-int soda_cuda_plan_create(const int32_t* extent, const soda_cuda_opts* opts,
+SODA_CUDA_API int soda_cuda_plan_create(const int32_t* extent, const soda_cuda_opts* opts,
                           soda_cuda_plan** plan);
-int soda_cuda_plan_destroy(soda_cuda_plan* plan);
+SODA_CUDA_API int soda_cuda_plan_destroy(soda_cuda_plan* plan);
 
 /* Host arrays through a plan (pinned or pageable memory). */
-int soda_cuda_plan_run_host(soda_cuda_plan* plan,
+SODA_CUDA_API int soda_cuda_plan_run_host(soda_cuda_plan* plan,
                             const void* const* in_ptrs, const int32_t* const* in_strides,
                             void* const* out_ptrs, const int32_t* const* out_strides);
 
 /* Device arrays through a plan: all `iterate` iterations, asynchronous on the
  * plan's stream.  pitches[t][0] = elements between rows, pitches[t][1] = between
  * planes (3-D).  Base addresses and row pitches must be 16-byte aligned. */
-int soda_cuda_plan_run_device(soda_cuda_plan* plan,
+SODA_CUDA_API int soda_cuda_plan_run_device(soda_cuda_plan* plan,
                               const void* const* d_in, const int64_t (*in_pitches)[2],
                               void* const* d_out, const int64_t (*out_pitches)[2]);
 
 /* One pass on caller-owned device buffers (used by the multi-GPU slab runtime,
  * which exchanges halos between passes).  `extent` is the extent of the local
  * arrays; outputs are written inside [box_lo[o], box_hi[o]) only. */
-int soda_cuda_run_pass(int32_t pass_index, const int32_t* extent,
+SODA_CUDA_API int soda_cuda_run_pass(int32_t pass_index, const int32_t* extent,
                        const void* const* d_in, const int64_t (*in_pitches)[2],
                        void* const* d_out, const int64_t (*out_pitches)[2],
                        const int32_t (*box_lo)[SODA_CUDA_MAX_DIM],
@@ -149,7 +157,7 @@ int soda_cuda_run_pass(int32_t pass_index, const int32_t* extent,
                        const soda_cuda_opts* opts);
 
 /* Number of kernel launches issued by this library since it was loaded. */
-int64_t soda_cuda_launch_count(void);
+SODA_CUDA_API int64_t soda_cuda_launch_count(void);
 
 #ifdef __cplusplus
 }  /* extern "C" */

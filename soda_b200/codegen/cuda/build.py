@@ -24,7 +24,10 @@ def nvcc_path() -> str:
 
 
 def nvcc_flags(strict_fp: bool = True, extra: Optional[List[str]] = None):
-  flags = ['-std=c++17', '-O3', '-lineinfo', '-shared', '-Xcompiler', '-fPIC'
+  flags = ['-std=c++17', '-O3', '-lineinfo', '-shared', '-Xcompiler', '-fPIC',
+           # several program libraries share one process: keep template
+           # statics and kernels private to each library
+           '-Xcompiler', '-fvisibility=hidden', '-Xcompiler', '-fno-gnu-unique'
           ] + ARCH_FLAGS
   # the reference's results are those of g++ without FMA contraction; keep
   # float arithmetic un-contracted unless the user opts out

@@ -330,7 +330,7 @@ def emit_program(stencil,
   params.append('const soda_cuda_opts* opts')
   lines.append('// reference: soda::app::%s (src/soda/codegen/frt/host.py:62-89)' %
                stencil.app_name)
-  lines.append('extern "C" int soda_cuda_%s(\n    %s) {' %
+  lines.append('extern "C" SODA_CUDA_API int soda_cuda_%s(\n    %s) {' %
                (stencil.app_name, ',\n    '.join(params)))
   first = stencil.input_stmts[0].name
   for stmt in stencil.input_stmts + stencil.output_stmts:

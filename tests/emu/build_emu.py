@@ -29,7 +29,7 @@ def build_emu_library(stencil, time_block=None, options=None,
     fp.write(source)
   cmd = [
       'g++', '-std=c++20', '-O1', '-g', '-shared', '-fPIC', '-pthread',
-      '-DSODA_EMU', '-ffp-contract=off', '-Wno-unknown-pragmas', '-I', HERE,
+      '-DSODA_EMU', '-ffp-contract=off', '-fvisibility=hidden', '-fno-gnu-unique', '-Wno-unknown-pragmas', '-I', HERE,
       '-I', build.CSRC_DIR, '-I', build.INCLUDE_DIR, base + '.cpp', '-o',
       lib + '.tmp'
   ]
