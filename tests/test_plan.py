@@ -1,0 +1,86 @@
+"""Planner tables: lags, register-window depths, halos, pass schedule."""
+import pytest
+
+from soda_b200 import util
+from soda_b200.codegen.cuda import emit, plan
+from tests import common
+
+
+def test_jacobi2d_time_block_4():
+  p = plan.make_pass_plan(common.stencil('jacobi2d', iterate=64), time_block=4)
+  assert [n.name for n in p.nodes][:2] == ['t1', 't1_iter1']
+  assert [n.lag for n in p.nodes] == [0, 1, 2, 3, 4]
+  # every level but the last is read at rows -1, 0, +1 by the next level
+  assert [n.ring for n in p.nodes] == [3, 3, 3, 3, 1]
+  assert p.nodes[-1].out == 0 and all(n.out < 0 for n in p.nodes[:-1])
+  assert (p.cells, p.strip) == (4, 128)
+  assert p.halo_lo == (4,) and p.halo_hi == (4,) and p.valid == (120,)
+  assert (p.lo_s, p.max_lag) == (-4, 4)
+
+
+def test_one_sided_window_blur():
+  p = plan.make_pass_plan(common.stencil('blur'))
+  # uint16: 8 cells per lane (16-byte vectors, 16-byte aligned TMA boxes)
+  assert (p.cells, p.strip, p.align0) == (8, 256, 8)
+  assert p.halo_lo == (0,) and p.halo_hi == (2,)
+  assert p.valid == (248,)
+  by_name = {n.name: n for n in p.nodes}
+  assert by_name['blur_x'].lag == 2 and by_name['blur_y'].lag == 2
+  assert by_name['input'].ring == 3 and by_name['blur_x'].ring == 1
+
+
+def test_off_centre_store_xcorr():
+  """tmp1(0, 9) = sum input(0, 0..18): offsets are taken relative to the store
+  index (src/soda/codegen/frt/host.py:587-592)."""
+  p = plan.make_pass_plan(common.stencil('xcorr'))
+  by_name = {n.name: n for n in p.nodes}
+  assert by_name['tmp1'].lag == 9 and by_name['input'].ring == 19
+  assert by_name['tmp2'].halo_lo == (9,) and by_name['tmp2'].halo_hi == (9,)
+  assert by_name['tmp3'].win_lo == (-9, -9) and \
+      by_name['tmp3'].win_hi == (9, 9)
+
+
+def test_3d_shared_memory_planes():
+  p = plan.make_pass_plan(common.stencil('jacobi3d', iterate=32), time_block=2,
+                          rows=8)
+  t1, mid, out = p.nodes
+  # dimension-1 neighbours of the input come from the TMA ring (no skew); those
+  # of the fused intermediate from an exported plane, read one step late
+  assert t1.smem_depth == 2 and mid.smem_depth == 2
+  assert (t1.lag, mid.lag, out.lag) == (0, 1, 2)
+  assert p.valid == (120, 4) and p.halo_lo == (4, 2)
+
+
+def test_multi_input_dag_denoise3d():
+  p = plan.make_pass_plan(common.stencil('denoise3d'), rows=8)
+  by_name = {n.name: n for n in p.nodes}
+  assert by_name['f'].kind == 'input' and by_name['u'].kind == 'input'
+  out = by_name['output']
+  assert [p.nodes[i].name for i in out.prods] == ['u', 'g', 'f', 'r1']
+  assert out.win_lo == (-2, -2, -2) and out.win_hi == (2, 2, 2)
+  assert by_name['g'].smem_depth >= 2  # g(0, +-1, 0) crosses warps
+
+
+def test_pass_schedule_and_time_block_choice():
+  assert plan.pass_schedule(64, 4) == [4] * 16
+  assert plan.pass_schedule(10, 4) == [4, 4, 2]
+  assert plan.pass_schedule(1, 1) == [1]
+  assert plan.choose_time_block(common.stencil('denoise2d')) == 1
+  assert plan.choose_time_block(common.stencil('jacobi2d')) == 2
+  assert plan.choose_time_block(common.stencil('jacobi2d', iterate=64)) == 4
+  assert plan.choose_time_block(common.stencil('heat3d', iterate=32), 3) == 3
+
+
+def test_window_too_wide_for_a_strip():
+  with pytest.raises(util.SemanticError):
+    plan.make_pass_plan(common.stencil('jacobi2d', iterate=128),
+                        time_block=70)
+
+
+def test_generated_source_contains_no_kernels():
+  """Only functors and tables are generated; kernels are the templates."""
+  text = emit.emit_program(common.stencil('jacobi2d', iterate=64), 4)
+  assert '__global__' not in text and '<<<' not in text
+  assert 'soda::NodeDesc kNodes' in text and 'struct Stage<0>' in text
+  assert 'a.template ld<0, -1, 0, 0>()' in text
+  assert 'extern "C" SODA_CUDA_API int soda_cuda_jacobi2d(' in text
