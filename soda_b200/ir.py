@@ -621,7 +621,7 @@ class CPrinter:
 
 
 def to_reduction(expr: Node) -> Optional[Tuple]:
-  """Flattens ``a + (b + c)``-style trees into ``('+', a, b, c)``.
+  """Flattens ``a + (b + c)``-style trees into ``('+', (a, b, c))``.
 
   Returns None if ``expr`` is not a pure ``+`` or pure ``*`` reduction with at
   least two operands.  (reference call sites:
@@ -648,7 +648,7 @@ def to_reduction(expr: Node) -> Optional[Tuple]:
   operands = tuple(flatten(expr))
   if len(operands) < 2:
     return None
-  return (op,) + operands
+  return op, operands
 
 
 def from_reduction(op: str, operands: Iterable[Node]) -> Node:

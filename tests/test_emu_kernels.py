@@ -54,3 +54,15 @@ def test_2d_templates_under_emulation(name, kwargs):
 @pytest.mark.parametrize('name,kwargs', CASES_3D)
 def test_3d_templates_under_emulation(name, kwargs):
   run_case(name, **kwargs)
+
+
+@pytest.mark.parametrize('name,kwargs', [
+    ('jacobi2d', dict(extent=(150, 40), time_block=2, iterate=4, segment=16)),
+    ('seidel2d', dict(extent=(140, 30), time_block=2, iterate=2)),
+    ('heat3d', dict(extent=(40, 20, 12), time_block=2, iterate=2,
+                    options={'rows': 8})),
+])
+def test_computation_reuse_stages_under_emulation(name, kwargs):
+  """--computation-reuse adds cr_var stages; they are ordinary nodes of the
+  fused DAG (shared partial sums in registers / shuffles)."""
+  run_case(name, computation_reuse='yes', **kwargs)

@@ -153,3 +153,14 @@ def test_jacobi2d_large_linearity_property():
   want = common.oracle_outputs(st, {'t1': sub})['t0'][r:-r, r:-r]
   got = prog.run_host({'t1': a})['t0'][y0:y0 + 256, x0:x0 + 256]
   assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize('name,extent', [('jacobi2d', (777, 300)),
+                                         ('seidel2d', (500, 200)),
+                                         ('xcorr', (600, 100)),
+                                         ('heat3d', (200, 40, 30)),
+                                         ('jacobi3d', (150, 30, 40))])
+def test_computation_reuse_on_gpu(name, extent):
+  """The CR-rewritten program (cr_var stages) is bit-exact against the oracle
+  evaluating the same rewritten IR."""
+  run_case(name, extent=extent, seed=8, computation_reuse='yes')
