@@ -73,7 +73,8 @@ typedef struct soda_cuda_opts {
   int32_t device;        /* CUDA device ordinal; -1 = current device */
   void* stream;          /* cudaStream_t; NULL = the default stream */
   int32_t segment;       /* output slices per CTA along the streamed dimension; 0 = auto */
-  int32_t reserved[5];
+  int32_t reserved[5];   /* reserved[0]: chunks of the pipelined host path (copy/compute
+                          * overlap of soda_cuda_plan_run_host); 0 = auto, 1 = off */
 } soda_cuda_opts;
 
 /* One pass = one HBM round trip = `time_block` fused iterations. */

@@ -84,12 +84,16 @@ class ProgramInfo(ctypes.Structure):
   ]
 
 
-def make_opts(device: int = -1, stream: int = 0, segment: int = 0) -> Opts:
+def make_opts(device: int = -1, stream: int = 0, segment: int = 0,
+              host_chunks: int = 0) -> Opts:
+  """``host_chunks``: chunk count of the copy/compute pipeline used for host
+  arrays (0 = automatic, 1 = no pipelining)."""
   opts = Opts()
   opts.struct_size = ctypes.sizeof(Opts)
   opts.device = device
   opts.stream = stream or None
   opts.segment = segment
+  opts.reserved[0] = host_chunks
   return opts
 
 

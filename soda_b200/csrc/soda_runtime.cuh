@@ -394,6 +394,9 @@ struct soda_cuda_plan {
   // ping-pong scratch between passes, per output
   void* scratch[2][soda::rt::kMaxT];
   long long pitch[2];  // elements between rows / planes of every plan buffer
+  int host_chunks;     // requested chunk count of the pipelined host path, 0 = auto
+  cudaStream_t copy_in_stream;   // H2D of chunk k+1 overlaps compute of chunk k
+  cudaStream_t copy_out_stream;  // ... and D2H of chunk k-1
 };
 
 namespace soda {
@@ -421,50 +424,96 @@ inline void default_boxes(const ProgramDesc& prog, const int* extent,
   }
 }
 
-// All passes on device buffers; intermediates ping-pong through plan scratch.
-inline int run_passes(soda_cuda_plan* plan, const void* const* d_in,
-                      const long long (*in_pitch)[2], void* const* d_out,
-                      const long long (*out_pitch)[2]) {
+// All passes for the output slices [s_begin, s_end) of the streamed dimension,
+// on the sub-array [s_begin - reach_lo, s_end + reach_hi) of the device buffers
+// (reach = what all passes together depend on).  Inside that window the
+// dependency cone of every kept cell is complete, so the result is identical
+// to running the whole grid at once; slices near the window edges compute
+// garbage that is never stored to the output.  Intermediates ping-pong through
+// the plan's scratch arrays (same window).
+inline int run_passes_window(soda_cuda_plan* plan, const void* const* d_in,
+                             const long long (*in_pitch)[2], void* const* d_out,
+                             const long long (*out_pitch)[2], int s_begin,
+                             int s_end) {
   const ProgramDesc& prog = soda_program();
+  const int dim = prog.info.dim, s_dim = dim - 1;
   const int num_passes = prog.info.num_passes;
   const int n_in = prog.info.num_inputs, n_out = prog.info.num_outputs;
+  int reach_lo = 0, reach_hi = 0;
+  for (int pass = 0; pass < num_passes; ++pass) {
+    const soda_cuda_pass_info& info = prog.impls[prog.schedule[pass]].info;
+    reach_lo += -info.reach_lo[s_dim];
+    reach_hi += info.reach_hi[s_dim];
+  }
+  const int total = plan->extent[s_dim];
+  const int view_lo = s_begin - reach_lo > 0 ? s_begin - reach_lo : 0;
+  const int view_hi = s_end + reach_hi < total ? s_end + reach_hi : total;
+  auto offset = [&](const void* base, const long long* pitch, int elem_bytes) {
+    const long long slice_pitch = dim == 2 ? pitch[0] : pitch[1];
+    return static_cast<const char*>(base) +
+           static_cast<long long>(view_lo) * slice_pitch * elem_bytes;
+  };
   for (int pass = 0; pass < num_passes; ++pass) {
     const bool first = pass == 0, last = pass == num_passes - 1;
     PassArgs a;
     memset(&a, 0, sizeof(a));
-    for (int d = 0; d < prog.info.dim; ++d) a.extent[d] = plan->extent[d];
+    for (int d = 0; d < dim; ++d) a.extent[d] = plan->extent[d];
+    a.extent[s_dim] = view_hi - view_lo;
     a.segment = plan->segment;
     a.stream = plan->stream;
     for (int i = 0; i < n_in; ++i) {
+      // pass inputs after the first are the previous pass's outputs
+      const int elem = first ? prog.in_elem_bytes[i] : prog.out_elem_bytes[i];
       if (first) {
-        a.in[i] = d_in[i];
+        a.in[i] = offset(d_in[i], in_pitch[i], elem);
         a.in_pitch[i][0] = in_pitch[i][0];
         a.in_pitch[i][1] = in_pitch[i][1];
       } else {
-        a.in[i] = plan->scratch[(pass - 1) & 1][i];
+        a.in[i] = offset(plan->scratch[(pass - 1) & 1][i], plan->pitch, elem);
         a.in_pitch[i][0] = plan->pitch[0];
         a.in_pitch[i][1] = plan->pitch[1];
       }
     }
     for (int o = 0; o < n_out; ++o) {
       if (last) {
-        a.out[o] = d_out[o];
+        a.out[o] = const_cast<char*>(
+            offset(d_out[o], out_pitch[o], prog.out_elem_bytes[o]));
         a.out_pitch[o][0] = out_pitch[o][0];
         a.out_pitch[o][1] = out_pitch[o][1];
       } else {
         int status = plan_alloc(plan, &plan->scratch[pass & 1][o],
                                 prog.out_elem_bytes[o]);
         if (status != SODA_CUDA_OK) return status;
-        a.out[o] = plan->scratch[pass & 1][o];
+        a.out[o] = const_cast<char*>(offset(plan->scratch[pass & 1][o],
+                                            plan->pitch, prog.out_elem_bytes[o]));
         a.out_pitch[o][0] = plan->pitch[0];
         a.out_pitch[o][1] = plan->pitch[1];
       }
     }
     default_boxes(prog, plan->extent, last, a.box_lo, a.box_hi);
+    for (int o = 0; o < n_out; ++o) {
+      if (last) {
+        int lo = a.box_lo[o][s_dim] > s_begin ? a.box_lo[o][s_dim] : s_begin;
+        int hi = a.box_hi[o][s_dim] < s_end ? a.box_hi[o][s_dim] : s_end;
+        a.box_lo[o][s_dim] = lo - view_lo;
+        a.box_hi[o][s_dim] = (hi > lo ? hi : lo) - view_lo;
+      } else {
+        a.box_lo[o][s_dim] = 0;
+        a.box_hi[o][s_dim] = view_hi - view_lo;
+      }
+    }
     int status = prog.impls[prog.schedule[pass]].launch(a);
     if (status != SODA_CUDA_OK) return status;
   }
   return SODA_CUDA_OK;
+}
+
+inline int run_passes(soda_cuda_plan* plan, const void* const* d_in,
+                      const long long (*in_pitch)[2], void* const* d_out,
+                      const long long (*out_pitch)[2]) {
+  const ProgramDesc& prog = soda_program();
+  return run_passes_window(plan, d_in, in_pitch, d_out, out_pitch, 0,
+                           plan->extent[prog.info.dim - 1]);
 }
 
 inline int check_strides(const int32_t* stride, const int* extent, int dim,
@@ -483,7 +532,8 @@ inline int check_strides(const int32_t* stride, const int* extent, int dim,
 }
 
 // Copies the box [lo, hi) between a strided host array and a plan buffer.
-inline int copy_box(const soda_cuda_plan* plan, int dim, void* device,
+inline int copy_box(const soda_cuda_plan* plan, cudaStream_t stream, int dim,
+                    void* device,
                     void* host, const int32_t* host_stride, int elem_bytes,
                     const int* lo, const int* hi, bool to_device) {
   long long hs[kMaxD] = {1, plan->extent[0],
@@ -499,11 +549,11 @@ inline int copy_box(const soda_cuda_plan* plan, int dim, void* device,
     if (to_device) {
       SODA_CUDA_CHECK(cudaMemcpy2DAsync(d_ptr, plan->pitch[0] * elem_bytes, h_ptr,
                                         hs[1] * elem_bytes, width, rows,
-                                        cudaMemcpyHostToDevice, plan->stream));
+                                        cudaMemcpyHostToDevice, stream));
     } else {
       SODA_CUDA_CHECK(cudaMemcpy2DAsync(h_ptr, hs[1] * elem_bytes, d_ptr,
                                         plan->pitch[0] * elem_bytes, width, rows,
-                                        cudaMemcpyDeviceToHost, plan->stream));
+                                        cudaMemcpyDeviceToHost, stream));
     }
     return SODA_CUDA_OK;
   }
@@ -524,7 +574,7 @@ inline int copy_box(const soda_cuda_plan* plan, int dim, void* device,
   parms.dstPos = pos;
   parms.extent = make_cudaExtent(width, hi[1] - lo[1], hi[2] - lo[2]);
   parms.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-  SODA_CUDA_CHECK(cudaMemcpy3DAsync(&parms, plan->stream));
+  SODA_CUDA_CHECK(cudaMemcpy3DAsync(&parms, stream));
   return SODA_CUDA_OK;
 }
 
@@ -590,6 +640,7 @@ int soda_cuda_plan_create(const int32_t* extent, const soda_cuda_opts* opts,
     plan->device = opts->device;
     plan->stream = static_cast<cudaStream_t>(opts->stream);
     plan->segment = opts->segment;
+    plan->host_chunks = opts->reserved[0];
   }
   if (plan->device < 0) {
     cudaError_t err = cudaGetDevice(&plan->device);
@@ -618,6 +669,8 @@ int soda_cuda_plan_destroy(soda_cuda_plan* plan) {
     if (plan->scratch[0][i]) cudaFree(plan->scratch[0][i]);
     if (plan->scratch[1][i]) cudaFree(plan->scratch[1][i]);
   }
+  if (plan->copy_in_stream) cudaStreamDestroy(plan->copy_in_stream);
+  if (plan->copy_out_stream) cudaStreamDestroy(plan->copy_out_stream);
   delete plan;
   return SODA_CUDA_OK;
 }
@@ -673,9 +726,6 @@ int soda_cuda_plan_run_host(soda_cuda_plan* plan, const void* const* in_ptrs,
     if (status != SODA_CUDA_OK) return status;
     status = plan_alloc(plan, &plan->d_in[i], prog.in_elem_bytes[i]);
     if (status != SODA_CUDA_OK) return status;
-    status = copy_box(plan, dim, plan->d_in[i], const_cast<void*>(in_ptrs[i]),
-                      stride, prog.in_elem_bytes[i], zero, plan->extent, true);
-    if (status != SODA_CUDA_OK) return status;
   }
   for (int o = 0; o < prog.info.num_outputs; ++o) {
     if (out_ptrs[o] == nullptr) return fail(SODA_CUDA_BAD_ARGUMENT, "NULL output");
@@ -685,21 +735,141 @@ int soda_cuda_plan_run_host(soda_cuda_plan* plan, const void* const* in_ptrs,
     status = plan_alloc(plan, &plan->d_out[o], prog.out_elem_bytes[o]);
     if (status != SODA_CUDA_OK) return status;
   }
-  status = run_passes(plan, plan->d_in, pitches, plan->d_out, pitches);
-  if (status != SODA_CUDA_OK) return status;
-  // only the valid interior goes back; the rest of the caller's array is untouched
+  // ---- chunked pipeline along the streamed dimension ----------------------
+  // chunk k: H2D (copy-in stream) -> all passes on its window (plan stream) ->
+  // D2H of its valid interior (copy-out stream); the copies of neighbouring
+  // chunks overlap the compute.  Chunks overlap by the total reach of all
+  // passes, so the price is (reach / chunk) redundant compute.
+  const int s_dim = dim - 1;
+  const int total = plan->extent[s_dim];
+  int reach = 0;
+  for (int pass = 0; pass < prog.info.num_passes; ++pass) {
+    const soda_cuda_pass_info& info = prog.impls[prog.schedule[pass]].info;
+    reach += info.reach_hi[s_dim] - info.reach_lo[s_dim];
+  }
+  long long bytes = 0;
+  for (int i = 0; i < prog.info.num_inputs; ++i)
+    bytes += plan_cells(plan, dim) * prog.in_elem_bytes[i];
+  int chunks = plan->host_chunks;
+  if (chunks <= 0) {
+    chunks = 1;
+    if (bytes >= (32LL << 20)) {
+      chunks = total / (8 * (reach > 0 ? reach : 1));
+      if (chunks > 16) chunks = 16;
+      if (chunks < 1) chunks = 1;
+    }
+  }
+  if (chunks > total) chunks = total;
+
   int lo[kMaxT][kMaxD], hi[kMaxT][kMaxD];
   default_boxes(prog, plan->extent, true, lo, hi);
-  for (int o = 0; o < prog.info.num_outputs; ++o) {
-    bool empty = false;
-    for (int d = 0; d < dim; ++d) empty = empty || hi[o][d] <= lo[o][d];
-    if (empty) continue;
-    status = copy_box(plan, dim, plan->d_out[o], out_ptrs[o],
-                      out_strides ? out_strides[o] : nullptr,
-                      prog.out_elem_bytes[o], lo[o], hi[o], false);
+  if (chunks == 1) {
+    for (int i = 0; i < prog.info.num_inputs; ++i) {
+      status = copy_box(plan, plan->stream, dim, plan->d_in[i],
+                        const_cast<void*>(in_ptrs[i]),
+                        in_strides ? in_strides[i] : nullptr,
+                        prog.in_elem_bytes[i], zero, plan->extent, true);
+      if (status != SODA_CUDA_OK) return status;
+    }
+    status = run_passes(plan, plan->d_in, pitches, plan->d_out, pitches);
     if (status != SODA_CUDA_OK) return status;
+    // only the valid interior goes back; the rest of the caller's array is
+    // untouched
+    for (int o = 0; o < prog.info.num_outputs; ++o) {
+      bool empty = false;
+      for (int d = 0; d < dim; ++d) empty = empty || hi[o][d] <= lo[o][d];
+      if (empty) continue;
+      status = copy_box(plan, plan->stream, dim, plan->d_out[o], out_ptrs[o],
+                        out_strides ? out_strides[o] : nullptr,
+                        prog.out_elem_bytes[o], lo[o], hi[o], false);
+      if (status != SODA_CUDA_OK) return status;
+    }
+    SODA_CUDA_CHECK(cudaStreamSynchronize(plan->stream));
+    return SODA_CUDA_OK;
   }
-  SODA_CUDA_CHECK(cudaStreamSynchronize(plan->stream));
+
+  if (plan->copy_in_stream == nullptr) {
+    SODA_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->copy_in_stream,
+                                              cudaStreamNonBlocking));
+    SODA_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->copy_out_stream,
+                                              cudaStreamNonBlocking));
+  }
+  std::vector<int> bound(chunks + 1);
+  for (int k = 0; k <= chunks; ++k)
+    bound[k] = static_cast<int>(static_cast<long long>(total) * k / chunks);
+  std::vector<cudaEvent_t> copied(chunks), computed(chunks);
+  for (int k = 0; k < chunks; ++k) {
+    SODA_CUDA_CHECK(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
+    SODA_CUDA_CHECK(cudaEventCreateWithFlags(&computed[k], cudaEventDisableTiming));
+  }
+  int result = SODA_CUDA_OK;
+  // the copy-in stream must not run ahead of work already queued on the plan
+  // stream that still reads the staging buffers (a previous call)
+  cudaEvent_t start_event;
+  SODA_CUDA_CHECK(cudaEventCreateWithFlags(&start_event, cudaEventDisableTiming));
+  SODA_CUDA_CHECK(cudaEventRecord(start_event, plan->stream));
+  SODA_CUDA_CHECK(cudaStreamWaitEvent(plan->copy_in_stream, start_event, 0));
+  for (int k = 0; k < chunks && result == SODA_CUDA_OK; ++k) {
+    int c_lo[kMaxD] = {0, 0, 0}, c_hi[kMaxD];
+    for (int d = 0; d < dim; ++d) c_hi[d] = plan->extent[d];
+    c_lo[s_dim] = bound[k];
+    c_hi[s_dim] = bound[k + 1];
+    for (int i = 0; i < prog.info.num_inputs && result == SODA_CUDA_OK; ++i)
+      result = copy_box(plan, plan->copy_in_stream, dim, plan->d_in[i],
+                        const_cast<void*>(in_ptrs[i]),
+                        in_strides ? in_strides[i] : nullptr,
+                        prog.in_elem_bytes[i], c_lo, c_hi, true);
+    if (result == SODA_CUDA_OK &&
+        cudaEventRecord(copied[k], plan->copy_in_stream) != cudaSuccess)
+      result = fail(SODA_CUDA_CUDA_ERROR, "cudaEventRecord failed");
+  }
+  int reach_hi_total = 0;
+  for (int pass = 0; pass < prog.info.num_passes; ++pass)
+    reach_hi_total += prog.impls[prog.schedule[pass]].info.reach_hi[s_dim];
+  for (int k = 0; k < chunks && result == SODA_CUDA_OK; ++k) {
+    // the window of chunk k ends at bound[k+1] + reach_hi: wait for the last
+    // chunk it touches (copies are issued in order on one stream)
+    int last_needed = k;
+    while (last_needed + 1 < chunks &&
+           bound[last_needed + 1] < bound[k + 1] + reach_hi_total)
+      ++last_needed;
+    if (cudaStreamWaitEvent(plan->stream, copied[last_needed], 0) != cudaSuccess)
+      result = fail(SODA_CUDA_CUDA_ERROR, "cudaStreamWaitEvent failed");
+    if (result == SODA_CUDA_OK)
+      result = run_passes_window(plan, plan->d_in, pitches, plan->d_out, pitches,
+                                 bound[k], bound[k + 1]);
+    if (result != SODA_CUDA_OK) break;
+    if (cudaEventRecord(computed[k], plan->stream) != cudaSuccess ||
+        cudaStreamWaitEvent(plan->copy_out_stream, computed[k], 0) != cudaSuccess)
+      result = fail(SODA_CUDA_CUDA_ERROR, "event synchronisation failed");
+    for (int o = 0; o < prog.info.num_outputs && result == SODA_CUDA_OK; ++o) {
+      int o_lo[kMaxD], o_hi[kMaxD];
+      bool empty = false;
+      for (int d = 0; d < dim; ++d) {
+        o_lo[d] = lo[o][d];
+        o_hi[d] = hi[o][d];
+      }
+      if (o_lo[s_dim] < bound[k]) o_lo[s_dim] = bound[k];
+      if (o_hi[s_dim] > bound[k + 1]) o_hi[s_dim] = bound[k + 1];
+      for (int d = 0; d < dim; ++d) empty = empty || o_hi[d] <= o_lo[d];
+      if (empty) continue;
+      result = copy_box(plan, plan->copy_out_stream, dim, plan->d_out[o],
+                        out_ptrs[o], out_strides ? out_strides[o] : nullptr,
+                        prog.out_elem_bytes[o], o_lo, o_hi, false);
+    }
+  }
+  cudaError_t sync_in = cudaStreamSynchronize(plan->copy_in_stream);
+  cudaError_t sync_compute = cudaStreamSynchronize(plan->stream);
+  cudaError_t sync_out = cudaStreamSynchronize(plan->copy_out_stream);
+  for (int k = 0; k < chunks; ++k) {
+    cudaEventDestroy(copied[k]);
+    cudaEventDestroy(computed[k]);
+  }
+  cudaEventDestroy(start_event);
+  if (result != SODA_CUDA_OK) return result;
+  SODA_CUDA_CHECK(sync_in);
+  SODA_CUDA_CHECK(sync_compute);
+  SODA_CUDA_CHECK(sync_out);
   return SODA_CUDA_OK;
 }
 

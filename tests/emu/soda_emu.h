@@ -54,6 +54,23 @@ inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+// everything is synchronous in the emulation, so streams and events are inert
+typedef void* cudaEvent_t;
+constexpr unsigned cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2;
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
+  *s = reinterpret_cast<cudaStream_t>(0x1);
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) {
+  *e = reinterpret_cast<cudaEvent_t>(0x1);
+  return cudaSuccess;
+}
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) {
+  return cudaSuccess;
+}
 inline cudaError_t cudaMalloc(void** ptr, size_t bytes) {
   // device buffers are deliberately filled with junk: the templates must never
   // let uninitialised scratch reach a stored cell

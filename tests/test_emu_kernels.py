@@ -12,7 +12,7 @@ from tests.emu import build_emu
 
 
 def run_case(name, extent=None, time_block=None, options=None, segment=0,
-             seed=1, **overrides):
+             seed=1, host_chunks=0, **overrides):
   st = common.stencil(name, **overrides)
   prog = launcher.CudaProgram(
       build_emu.build_emu_library(st, time_block=time_block, options=options))
@@ -22,7 +22,9 @@ def run_case(name, extent=None, time_block=None, options=None, segment=0,
       n: np.full(extent[::-1], 77, dtype=d)
       for n, d in zip(prog.output_names, prog.output_dtypes)
   }
-  prog.run_host(inputs, outputs, opts=launcher.make_opts(segment=segment))
+  prog.run_host(inputs, outputs,
+                opts=launcher.make_opts(segment=segment,
+                                        host_chunks=host_chunks))
   common.assert_matches_oracle(st, extent, outputs,
                                common.oracle_outputs(st, inputs), sentinel=77)
 
@@ -66,3 +68,16 @@ def test_computation_reuse_stages_under_emulation(name, kwargs):
   """--computation-reuse adds cr_var stages; they are ordinary nodes of the
   fused DAG (shared partial sums in registers / shuffles)."""
   run_case(name, computation_reuse='yes', **kwargs)
+
+
+@pytest.mark.parametrize('name,kwargs', [
+    ('jacobi2d', dict(extent=(150, 60), time_block=2, iterate=5, segment=16)),
+    ('denoise2d', dict(extent=(64, 40))),
+    ('heat3d', dict(extent=(40, 12, 20), time_block=2, iterate=4,
+                    options={'rows': 8})),
+    ('jacobi2d', dict(extent=(40, 7), time_block=2)),  # chunks thinner than reach
+])
+def test_pipelined_host_path_under_emulation(name, kwargs):
+  """soda_cuda_plan_run_host cuts the grid into overlapping chunks along the
+  streamed dimension so that copies overlap compute; results must not change."""
+  run_case(name, host_chunks=3, **kwargs)

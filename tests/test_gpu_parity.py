@@ -17,7 +17,7 @@ SENTINELS = {'f': 77.0, 'i': 77, 'u': 77}
 
 
 def run_case(name, extent=None, seed=0, pattern='random', time_block=None,
-             options=None, segment=0, **overrides):
+             options=None, segment=0, host_chunks=0, **overrides):
   st = common.stencil(name, **overrides)
   prog = cuda_backend.compile_stencil(st, time_block=time_block,
                                       options=options)
@@ -28,8 +28,12 @@ def run_case(name, extent=None, seed=0, pattern='random', time_block=None,
       for n, d in zip(prog.output_names, prog.output_dtypes)
   }
   before = prog.launch_count()
-  prog.run_host(inputs, outputs, opts=launcher.make_opts(segment=segment))
-  assert prog.num_passes - 1 <= prog.launch_count() - before <= prog.num_passes
+  prog.run_host(inputs, outputs,
+                opts=launcher.make_opts(segment=segment,
+                                        host_chunks=host_chunks))
+  launches = prog.launch_count() - before
+  chunks = max(1, host_chunks)
+  assert (prog.num_passes - 1) * chunks <= launches <= prog.num_passes * chunks
   want = common.oracle_outputs(st, inputs)
   common.assert_matches_oracle(st, extent, outputs, want, sentinel=77)
   return prog
@@ -164,3 +168,28 @@ def test_computation_reuse_on_gpu(name, extent):
   """The CR-rewritten program (cr_var stages) is bit-exact against the oracle
   evaluating the same rewritten IR."""
   run_case(name, extent=extent, seed=8, computation_reuse='yes')
+
+
+@pytest.mark.parametrize('name,extent,kwargs', [
+    ('jacobi2d', (1000, 900), dict(iterate=11, time_block=4)),
+    ('blur', (2000, 512), dict(iterate=2)),
+    ('denoise2d', (500, 300), {}),
+    ('heat3d', (200, 40, 90), dict(iterate=5, time_block=2)),
+])
+def test_pipelined_host_path(name, extent, kwargs):
+  """Chunked H2D / compute / D2H overlap must not change any stored cell."""
+  run_case(name, extent=extent, seed=12, host_chunks=4, **kwargs)
+
+
+def test_pipelined_host_path_auto_chunks_large_grid():
+  """> 32 MiB of input switches the pipeline on by default."""
+  st = common.stencil('jacobi2d', iterate=8)
+  prog = cuda_backend.compile_stencil(st, time_block=4)
+  extent = (4096, 4096)
+  rng = np.random.default_rng(4)
+  a = rng.random(extent[::-1], dtype=np.float32)
+  before = prog.launch_count()
+  piped = prog.run_host({'t1': a})['t0']
+  assert prog.launch_count() - before > prog.num_passes  # several chunks ran
+  plain = prog.run_host({'t1': a}, opts=launcher.make_opts(host_chunks=1))['t0']
+  assert np.array_equal(piped.view(np.uint32), plain.view(np.uint32))
