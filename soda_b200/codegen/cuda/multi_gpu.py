@@ -106,41 +106,47 @@ class SlabRunner:
     return tensor[..., :self.global_extent[0]]
 
   # -- halo exchange ----------------------------------------------------------------
-  def exchange(self, tensors: Sequence[torch.Tensor], reach_lo: int,
-               reach_hi: int) -> None:
-    """Fills the ghost slices of ``tensors`` from the neighbouring ranks.
+  def _comm_view(self, tensor: torch.Tensor) -> torch.Tensor:
+    """NCCL has no unsigned 16/32/64-bit types: exchange the same bits as a
+    signed type."""
+    alias = {torch.uint16: torch.int16, torch.uint32: torch.int32,
+             torch.uint64: torch.int64}
+    return tensor.view(alias[tensor.dtype]) if tensor.dtype in alias else tensor
+
+  def start_exchange(self, tensors: Sequence[torch.Tensor], reach_lo: int,
+                     reach_hi: int):
+    """Starts filling the ghost slices of ``tensors`` from the neighbouring
+    ranks and returns the pending work handles.
 
     A rank's lower ghost (``reach_lo`` slices) comes from the top of the rank
     below; its upper ghost (``reach_hi`` slices) from the bottom of the rank
-    above.
+    above.  The transfers are ordered after everything already queued on the
+    current stream and run beside what is queued afterwards.
     """
     ops = []
     lo, hi = self.own
-    keep = []
     for tensor in tensors:
+      tensor = self._comm_view(tensor)
       if self.rank > 0:
         if reach_hi > 0:  # the lower neighbour's upper ghost is my bottom rows
-          send = tensor[lo:lo + reach_hi].contiguous()
-          keep.append(send)
-          ops.append(dist.P2POp(dist.isend, send, self._peer(self.rank - 1),
-                                self.group))
+          ops.append(dist.P2POp(dist.isend, tensor[lo:lo + reach_hi],
+                                self._peer(self.rank - 1), self.group))
         if reach_lo > 0:
-          recv = tensor[lo - reach_lo:lo]
-          ops.append(dist.P2POp(dist.irecv, recv, self._peer(self.rank - 1),
-                                self.group))
+          ops.append(dist.P2POp(dist.irecv, tensor[lo - reach_lo:lo],
+                                self._peer(self.rank - 1), self.group))
       if self.rank < self.world - 1:
         if reach_lo > 0:  # the upper neighbour's lower ghost is my top rows
-          send = tensor[hi - reach_lo:hi].contiguous()
-          keep.append(send)
-          ops.append(dist.P2POp(dist.isend, send, self._peer(self.rank + 1),
-                                self.group))
+          ops.append(dist.P2POp(dist.isend, tensor[hi - reach_lo:hi],
+                                self._peer(self.rank + 1), self.group))
         if reach_hi > 0:
-          recv = tensor[hi:hi + reach_hi]
-          ops.append(dist.P2POp(dist.irecv, recv, self._peer(self.rank + 1),
-                                self.group))
-    if ops:
-      for work in dist.batch_isend_irecv(ops):
-        work.wait()
+          ops.append(dist.P2POp(dist.irecv, tensor[hi:hi + reach_hi],
+                                self._peer(self.rank + 1), self.group))
+    return dist.batch_isend_irecv(ops) if ops else []
+
+  def exchange(self, tensors: Sequence[torch.Tensor], reach_lo: int,
+               reach_hi: int) -> None:
+    for work in self.start_exchange(tensors, reach_lo, reach_hi):
+      work.wait()
 
   def _peer(self, rank: int) -> int:
     if self.group is None:
@@ -171,18 +177,32 @@ class SlabRunner:
       hi_boxes.append(hi)
     return lo_boxes, hi_boxes
 
-  def run(self) -> None:
+  def _launch(self, index, current, target, box_lo, box_hi, opts) -> None:
+    pitches = self._pitches()
+    self.program.run_pass(index, self.local_extent,
+                          [t.data_ptr() for t in current],
+                          [pitches] * len(current),
+                          [t.data_ptr() for t in target],
+                          [pitches] * len(target), box_lo, box_hi, opts)
+    self.launches += 1
+
+  def run(self, overlap: bool = True) -> None:
     """All ``iterate`` iterations: ``self.inputs`` -> ``self.outputs``.  The
     ghost slices of ``self.inputs`` are refreshed first, so callers only fill
-    the slices they own."""
+    the slices they own.
+
+    With ``overlap`` every pass but the last is issued as three launches: the
+    slices next to each slab boundary (what the neighbours need for the next
+    pass) first, then the halo exchange of those slices is started, then the
+    interior is computed while the exchange is in flight.
+    """
     prog = self.program
     opts = launcher.make_opts(stream=self.stream_handle)
-    pitches = self._pitches()
+    s_dim = self.dim - 1
     current = self.inputs
+    self.exchange(current, *self.pass_reach[0])
     for index in range(prog.num_passes):
       last = index == prog.num_passes - 1
-      reach_lo, reach_hi = self.pass_reach[index]
-      self.exchange(current, reach_lo, reach_hi)
       if last:
         target = self.outputs
       else:
@@ -192,10 +212,36 @@ class SlabRunner:
             bank[o] = self._alloc(dt)
         target = bank
       box_lo, box_hi = self._boxes(last)
-      prog.run_pass(index, self.local_extent,
-                    [t.data_ptr() for t in current],
-                    [pitches] * len(current),
-                    [t.data_ptr() for t in target], [pitches] * len(target),
-                    box_lo, box_hi, opts)
-      self.launches += 1
+      if last or self.world == 1:
+        self._launch(index, current, target, box_lo, box_hi, opts)
+        current = target
+        continue
+      next_lo, next_hi = self.pass_reach[index + 1]
+      own_lo, own_hi = self.own
+      # slices of this pass's output that a neighbour needs for the next pass
+      bottom = (own_lo, min(own_hi, own_lo + next_hi)) if self.rank > 0 \
+          else (own_lo, own_lo)
+      top = (max(bottom[1], own_hi - next_lo), own_hi) \
+          if self.rank < self.world - 1 else (own_hi, own_hi)
+      if not overlap:
+        bottom, top = (own_lo, own_lo), (own_hi, own_hi)
+
+      def restricted(lo_slice, hi_slice):
+        lo = [list(b) for b in box_lo]
+        hi = [list(b) for b in box_hi]
+        for o in range(len(lo)):
+          lo[o][s_dim] = max(lo[o][s_dim], lo_slice)
+          hi[o][s_dim] = max(lo[o][s_dim], min(hi[o][s_dim], hi_slice))
+        return lo, hi
+
+      for lo_slice, hi_slice in (bottom, top):
+        if hi_slice > lo_slice:
+          self._launch(index, current, target, *restricted(lo_slice, hi_slice),
+                       opts)
+      pending = self.start_exchange(target, next_lo, next_hi)
+      if top[0] > bottom[1]:
+        self._launch(index, current, target, *restricted(bottom[1], top[0]),
+                     opts)
+      for work in pending:
+        work.wait()
       current = target

@@ -117,6 +117,11 @@ __device__ __forceinline__ T shfl_rel(T v) {
   }
 }
 
+// warp-uniform OR of a per-lane flag
+__device__ __forceinline__ bool warp_any(bool flag) {
+  return __any_sync(kFullMask, flag) != 0;
+}
+
 __device__ __forceinline__ void warp_sync() { __syncwarp(); }
 __device__ __forceinline__ void cta_sync() { __syncthreads(); }
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

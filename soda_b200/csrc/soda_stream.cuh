@@ -145,17 +145,64 @@ __device__ __forceinline__ void eval_cells(Ctx& ctx) {
   }
 }
 
-// Stores the kCells cells a lane holds for one output row segment.
+// Per-lane store plan of one output, fixed for the whole strip / tile: which
+// cells of the lane's vector may be written, where slice 0 of the lane's
+// vector lives and how far consecutive slices are apart.  Computed once; the
+// per-step work is then one pointer bump, one slice-range test and one
+// (predicated) vector store.
+struct StorePlan {
+  unsigned char* ptr;   // address of the lane's vector in the current slice
+  long long step;       // bytes between consecutive slices
+  int slice_lo;         // slices [slice_lo, slice_hi) are stored
+  int slice_hi;
+  int mode;             // 0: nothing, 1: whole vector, 2: some cells (mask)
+  unsigned mask;        // cells to store when mode == 2
+};
+
 template <typename T, int kC>
-__device__ __forceinline__ void store_cells(T* dst, const T (&v)[kC], int col,
-                                            int box_lo, int box_hi,
-                                            bool vec_ok) {
-  if (vec_ok && col >= box_lo && col + kC <= box_hi) {
-    store_global_vec<T, kC>(dst, v);
+__device__ __forceinline__ void init_store_plan(StorePlan& plan, void* base,
+                                                long long offset_elems,
+                                                long long step_elems, int col,
+                                                bool lane_ok, int box_lo,
+                                                int box_hi, bool vec_ok,
+                                                int slice_lo, int slice_hi,
+                                                int first_slice) {
+  plan.step = step_elems * static_cast<long long>(sizeof(T));
+  plan.ptr = static_cast<unsigned char*>(base) +
+             (offset_elems + col + first_slice * step_elems) *
+                 static_cast<long long>(sizeof(T));
+  plan.slice_lo = slice_lo;
+  plan.slice_hi = slice_hi;
+  plan.mask = 0;
+#pragma unroll
+  for (int i = 0; i < kC; ++i) {
+    if (lane_ok && col + i >= box_lo && col + i < box_hi) plan.mask |= 1u << i;
+  }
+  if (plan.mask == 0) {
+    plan.mode = 0;
+  } else if (vec_ok && plan.mask == (1u << kC) - 1u) {
+    plan.mode = 1;
+  } else {
+    plan.mode = 2;
+  }
+}
+
+// Stores `v` as slice `slice` of the output and advances to the next slice.
+// `any_partial` is warp-uniform: only warps that touch an edge of the store box
+// take the per-cell path, everybody else issues a single predicated vector
+// store and the warp stays converged for the shuffles that follow.
+template <typename T, int kC>
+__device__ __forceinline__ void store_slice(StorePlan& plan, const T (&v)[kC],
+                                            int slice, bool any_partial) {
+  T* dst = reinterpret_cast<T*>(plan.ptr);
+  plan.ptr += plan.step;
+  if (slice < plan.slice_lo || slice >= plan.slice_hi) return;  // uniform
+  if (!any_partial) {
+    if (plan.mode == 1) store_global_vec<T, kC>(dst, v);
   } else {
 #pragma unroll
     for (int i = 0; i < kC; ++i) {
-      if (col + i >= box_lo && col + i < box_hi) dst[i] = v[i];
+      if ((plan.mask >> i) & 1u) dst[i] = v[i];
     }
   }
 }
@@ -216,29 +263,38 @@ struct Ctx2D {
   int x0;      // dimension-0 cell of the strip's first (lane 0) cell
   int seg_lo;  // output rows [seg_lo, seg_hi) belong to this warp
   int seg_hi;
+  StorePlan store[Prog::kNumOutputs];
+  bool any_partial;
 
   __device__ __forceinline__ explicit Ctx2D(const Params2D<Prog>& params)
       : p(params) {}
 };
 
+template <class Prog, int O = 0>
+__device__ __forceinline__ void init_stores_2d(Ctx2D<Prog>& ctx, int t_begin) {
+  if constexpr (O < Prog::kNumOutputs) {
+    constexpr int N = Prog::kOutputNode[O];
+    using T = typename Prog::template T<N>;
+    constexpr int kC = Prog::kCells;
+    const int col_in_strip = ctx.lane * kC;
+    const bool lane_ok = col_in_strip >= Prog::kHaloLo0 &&
+                         col_in_strip + kC <= Prog::kHaloLo0 + Prog::kValid0;
+    init_store_plan<T, kC>(
+        ctx.store[O], ctx.p.out[O], 0, ctx.p.out_pitch[O],
+        ctx.x0 + col_in_strip, lane_ok, ctx.p.box_lo[O][0], ctx.p.box_hi[O][0],
+        ctx.p.vec_ok != 0, max(ctx.seg_lo, ctx.p.box_lo[O][1]),
+        min(ctx.seg_hi, ctx.p.box_hi[O][1]), t_begin - Prog::kNodes[N].lag);
+    init_stores_2d<Prog, O + 1>(ctx, t_begin);
+  }
+}
+
 template <class Prog, class Ctx, int N>
 __device__ __forceinline__ void store_node_2d(Ctx& ctx, int t) {
   using T = typename Prog::template T<N>;
-  constexpr int kC = Prog::kCells;
   constexpr int kOut = Prog::kNodes[N].out;
-  const int row = t - Prog::kNodes[N].lag;
-  const int col_in_strip = ctx.lane * kC;
-  const bool lane_ok = col_in_strip >= Prog::kHaloLo0 &&
-                       col_in_strip + kC <= Prog::kHaloLo0 + Prog::kValid0;
-  const int lo = max(ctx.seg_lo, ctx.p.box_lo[kOut][1]);
-  const int hi = min(ctx.seg_hi, ctx.p.box_hi[kOut][1]);
-  if (row < lo || row >= hi || !lane_ok) return;
-  const int col = ctx.x0 + col_in_strip;
-  T* dst = static_cast<T*>(ctx.p.out[kOut]) +
-           static_cast<long long>(row) * ctx.p.out_pitch[kOut] + col;
-  store_cells<T, kC>(dst, ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1],
-                     col, ctx.p.box_lo[kOut][0], ctx.p.box_hi[kOut][0],
-                     ctx.p.vec_ok != 0);
+  store_slice<T, Prog::kCells>(
+      ctx.store[kOut], ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1],
+      t - Prog::kNodes[N].lag, ctx.any_partial);
 }
 
 // One step: every node of the pass DAG produces one row.  `r` is the row of
@@ -313,6 +369,14 @@ __global__ void __launch_bounds__(Prog::kWarps * 32, Prog::kMinBlocks)
       issue_chunk_2d<Prog>(p, slots + s * S::kSlotBytes, ctx.x0,
                            t_begin + s * kChunk, &full[s]);
     }
+  }
+  init_stores_2d<Prog>(ctx, t_begin);
+  {
+    bool partial = false;
+#pragma unroll
+    for (int o = 0; o < Prog::kNumOutputs; ++o)
+      partial = partial || ctx.store[o].mode == 2;
+    ctx.any_partial = warp_any(partial);
   }
   warp_sync();
 
@@ -410,6 +474,8 @@ struct Ctx3D {
   int step;      // steps since the start of the segment
   int x0, y0;
   int seg_lo, seg_hi;
+  StorePlan store[Prog::kNumOutputs];
+  bool any_partial;
 
   __device__ __forceinline__ explicit Ctx3D(const Params3D<Prog>& params)
       : p(params) {}
@@ -440,30 +506,36 @@ struct Ctx3D {
   }
 };
 
+template <class Prog, int O = 0>
+__device__ __forceinline__ void init_stores_3d(Ctx3D<Prog>& ctx, int t_begin) {
+  if constexpr (O < Prog::kNumOutputs) {
+    constexpr int N = Prog::kOutputNode[O];
+    using T = typename Prog::template T<N>;
+    constexpr int kC = Prog::kCells;
+    const int col_in_strip = ctx.lane * kC;
+    const int y = ctx.y0 + ctx.row;
+    const bool lane_ok =
+        col_in_strip >= Prog::kHaloLo0 &&
+        col_in_strip + kC <= Prog::kHaloLo0 + Prog::kValid0 &&
+        ctx.row >= Prog::kHaloLo1 && ctx.row < Prog::kHaloLo1 + Prog::kValid1 &&
+        y >= ctx.p.box_lo[O][1] && y < ctx.p.box_hi[O][1];
+    init_store_plan<T, kC>(
+        ctx.store[O], ctx.p.out[O],
+        static_cast<long long>(y) * ctx.p.out_pitch[O], ctx.p.out_plane_pitch[O],
+        ctx.x0 + col_in_strip, lane_ok, ctx.p.box_lo[O][0], ctx.p.box_hi[O][0],
+        ctx.p.vec_ok != 0, max(ctx.seg_lo, ctx.p.box_lo[O][2]),
+        min(ctx.seg_hi, ctx.p.box_hi[O][2]), t_begin - Prog::kNodes[N].lag);
+    init_stores_3d<Prog, O + 1>(ctx, t_begin);
+  }
+}
+
 template <class Prog, class Ctx, int N>
 __device__ __forceinline__ void store_node_3d(Ctx& ctx, int t) {
   using T = typename Prog::template T<N>;
-  constexpr int kC = Prog::kCells;
   constexpr int kOut = Prog::kNodes[N].out;
-  const int plane = t - Prog::kNodes[N].lag;
-  const int col_in_strip = ctx.lane * kC;
-  const bool lane_ok = col_in_strip >= Prog::kHaloLo0 &&
-                       col_in_strip + kC <= Prog::kHaloLo0 + Prog::kValid0;
-  const bool row_ok =
-      ctx.row >= Prog::kHaloLo1 && ctx.row < Prog::kHaloLo1 + Prog::kValid1;
-  const int lo = max(ctx.seg_lo, ctx.p.box_lo[kOut][2]);
-  const int hi = min(ctx.seg_hi, ctx.p.box_hi[kOut][2]);
-  const int y = ctx.y0 + ctx.row;
-  if (plane < lo || plane >= hi || !lane_ok || !row_ok ||
-      y < ctx.p.box_lo[kOut][1] || y >= ctx.p.box_hi[kOut][1])
-    return;
-  const int col = ctx.x0 + col_in_strip;
-  T* dst = static_cast<T*>(ctx.p.out[kOut]) +
-           static_cast<long long>(plane) * ctx.p.out_plane_pitch[kOut] +
-           static_cast<long long>(y) * ctx.p.out_pitch[kOut] + col;
-  store_cells<T, kC>(dst, ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1],
-                     col, ctx.p.box_lo[kOut][0], ctx.p.box_hi[kOut][0],
-                     ctx.p.vec_ok != 0);
+  store_slice<T, Prog::kCells>(
+      ctx.store[kOut], ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1],
+      t - Prog::kNodes[N].lag, ctx.any_partial);
 }
 
 template <class Prog, class Ctx, int N = 0>
@@ -538,6 +610,14 @@ __global__ void __launch_bounds__(Prog::kRows * 32, Prog::kMinBlocks)
       issue_plane_3d<Prog>(p, ring + s * S::kSlotBytes, ctx.x0, ctx.y0,
                            t_begin + s, &full[s]);
     }
+  }
+  init_stores_3d<Prog>(ctx, t_begin);
+  {
+    bool partial = false;
+#pragma unroll
+    for (int o = 0; o < Prog::kNumOutputs; ++o)
+      partial = partial || ctx.store[o].mode == 2;
+    ctx.any_partial = warp_any(partial);
   }
   cta_sync();
 

@@ -300,6 +300,18 @@ inline int lane_id() { return threadIdx.x & 31; }
 inline void warp_sync() { soda_emu_cta->warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }
 inline void cta_sync() { soda_emu_cta->cta_barrier.arrive_and_wait(); }
 
+inline bool warp_any(bool flag) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto& slots = soda_emu_cta->warp_slots[warp];
+  slots[lane] = flag ? 1 : 0;
+  warp_sync();
+  bool any = false;
+  const int lanes = std::min(32, soda_emu_cta->threads - warp * 32);
+  for (int l = 0; l < lanes; ++l) any = any || slots[l] != 0;
+  warp_sync();
+  return any;
+}
+
 template <int kDelta, typename T>
 inline T shfl_rel(T v) {
   static_assert(kDelta != 0 && kDelta > -32 && kDelta < 32, "bad lane delta");

@@ -41,7 +41,7 @@ def _worker(rank, world, port, name, overrides, time_block, extent, lib, seed,
     for tensor in runner.outputs:
       tensor.fill_(77)
     runner.run()
-    assert runner.launches == prog.num_passes
+    assert runner.launches >= prog.num_passes
     for tensor, oname in zip(runner.outputs, st.output_names):
       np.save(os.path.join(result_dir, '%s_%d.npy' % (oname, rank)),
               runner.view(tensor)[lo:hi].numpy())
