@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 WIDTH = 16384
 HEIGHT = 16384
 ITERATE = 64
-TIME_BLOCK = int(os.environ.get('SODA_BENCH_TIME_BLOCK', '4'))
+TIME_BLOCK = int(os.environ.get('SODA_BENCH_TIME_BLOCK', '5'))
 PROGRAM = 'jacobi2d'
 BYTES_PER_CELL_PER_PASS = 8  # one fp32 read + one fp32 write
 FALLBACK_HBM_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md
@@ -171,6 +171,8 @@ def run_reference(args, out):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
+  # torchrun pins OMP_NUM_THREADS=1 per rank; the baseline uses every core
+  os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
   sample_iterate = 4
   steps = max(1, args.steps)
   baseline = None

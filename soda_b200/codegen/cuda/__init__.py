@@ -49,6 +49,10 @@ def add_arguments(parser) -> None:
                       help='2-D rows per TMA box')
   parser.add_argument('--cuda-stages', type=int, dest='cuda_stages',
                       metavar='N', help='2-D TMA ring slots per warp')
+  parser.add_argument('--cuda-no-pack', action='store_true',
+                      dest='cuda_no_pack',
+                      help='do not use packed fp32 pairs (FADD2/FMUL2) for '
+                      'float add/mul programs')
   parser.add_argument('--cuda-fast-fp', action='store_true',
                       dest='cuda_fast_fp',
                       help='allow FMA contraction (default: off, results are '
@@ -64,6 +68,7 @@ def options_from_args(args: Optional[argparse.Namespace]) -> Dict:
       'chunk': get('cuda_chunk'),
       'stages': get('cuda_stages'),
       'fast_fp': bool(get('cuda_fast_fp')),
+      'no_pack': bool(get('cuda_no_pack')),
   }
   return {k: v for k, v in options.items() if v}
 

@@ -53,6 +53,11 @@ class _FunctorPrinter(ir.CPrinter):
   non-zero divisors."""
 
   def __call__(self, node):
+    if isinstance(node, ir.Cast):
+      # spelled so that the same functor text works for scalar cells and for
+      # packed fp32 pairs (soda::cast_to<float>(F2) is the identity)
+      return 'soda::cast_to<{}>({})'.format(node.haoda_type.c_type,
+                                            self(node.expr))
     if isinstance(node, ir.MulDiv) and not node.singleton and \
         not ir.result_type(node).is_float and \
         any(op in ('/', '%') for op in node.operator):
@@ -91,15 +96,13 @@ def _functor(desc: planner.StageDesc, dim: int) -> List[str]:
       '// {}'.format(str(stmt).replace('\n', '\n// ')),
       'template <> struct Stage<{}> {{'.format(desc.index),
       '  template <class A>',
-      '  static __device__ __forceinline__ {} eval(const A& a) {{'.format(
-          ctype),
+      '  static __device__ __forceinline__ auto eval(const A& a) {',
   ]
   for let in stmt.let:
-    lines.append('    const {} {} = {}({});'.format(let.haoda_type.c_type,
-                                                   let.name,
-                                                   let.haoda_type.c_type,
-                                                   printer(let.expr)))
-  lines.append('    return {}({});'.format(ctype, printer(stmt.expr)))
+    lines.append('    const auto {} = soda::cast_to<{}>({});'.format(
+        let.name, let.haoda_type.c_type, printer(let.expr)))
+  lines.append('    return soda::cast_to<{}>({});'.format(
+      ctype, printer(stmt.expr)))
   lines.append('  }')
   lines.append('};')
   return lines
@@ -175,6 +178,7 @@ def _emit_pass(ns: str, stencil, pass_plan: planner.PassPlan,
       'kHaloLo0': pass_plan.halo_lo[0],
       'kValid0': pass_plan.valid[0],
       'kAlign0': pass_plan.align0,
+      'kPack': pass_plan.pack,
       'kLoS': pass_plan.lo_s,
       'kMaxLag': pass_plan.max_lag,
   }
@@ -237,7 +241,8 @@ def emit_program(stencil,
       tb: planner.make_pass_plan(stencil,
                                  time_block=tb,
                                  cells=options.get('cells'),
-                                 rows=options.get('rows') or 8)
+                                 rows=options.get('rows') or 8,
+                                 pack=False if options.get('no_pack') else None)
       for tb in variants
   }
   stages = plans[variants[0]].stages

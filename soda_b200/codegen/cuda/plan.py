@@ -83,6 +83,7 @@ class PassPlan:
   max_lag: int
   rows: int = 1  # 3-D: tile rows (= warps per CTA)
   align0: int = 1  # strip origins are multiples of this many cells
+  pack: int = 1  # cells evaluated per instruction (2: packed fp32 pairs)
 
   @property
   def output_nodes(self) -> List[Node]:
@@ -141,10 +142,63 @@ def default_cells(stencil) -> int:
   return max(2, 128 // max(widest, 16))
 
 
+def packable(stencil) -> bool:
+  """Whether the program can be evaluated two cells at a time with packed fp32
+  instructions (FADD2 / FMUL2): every tensor is ``float`` and every statement
+  only adds, subtracts and multiplies loads, fp32 literals and integer
+  literals.  Anything else (division, calls, comparisons, double literals,
+  integer tensors) keeps the scalar path."""
+  float_t = ir.Type('float')
+  types = stencil.input_types + stencil.output_types + tuple(
+      stencil.local_types)
+  if any(t != float_t for t in types):
+    return False
+
+  def ok(node) -> bool:
+    if isinstance(node, ir.Operand):
+      return ok(node.inner)
+    if isinstance(node, (ir.Ref, ir.Var)):
+      return True
+    if isinstance(node, ir.Num):
+      return node.literal_type in (float_t, ir.INT32)
+    if isinstance(node, ir.Cast):
+      return node.haoda_type == float_t and ok(node.expr)
+    if isinstance(node, ir.Unary):
+      return all(op in '+-' for op in node.operator) and ok(node.operand)
+    if isinstance(node, ir.AddSub):
+      return all(ok(o) for o in node.operand)
+    if isinstance(node, ir.MulDiv):
+      return all(op == '*' for op in node.operator) and \
+          all(ok(o) for o in node.operand)
+    if isinstance(node, ir.BinaryOp) and node.singleton:
+      return ok(node.operand[0])
+    return False
+
+  for stmt in list(stencil.local_stmts) + list(stencil.output_stmts):
+    for let in stmt.let:
+      if let.haoda_type not in (None, float_t) or not ok(let.expr):
+        return False
+    if not ok(stmt.expr):
+      return False
+    # a load at an odd dimension-0 offset straddles two register pairs and
+    # costs moves to assemble; measured on B200 the packed path only pays off
+    # while there are at most two of them per statement (5/7-point stars:
+    # +9 % at time block 5-6; 9-point box: -8 %)
+    odd = {
+        tuple(a - b for a, b in zip(ref.idx, stmt.ref.idx))
+        for ref in _stmt_loads(stmt)
+        if (ref.idx[0] - stmt.ref.idx[0]) % 2
+    }
+    if len(odd) > 2:
+      return False
+  return True
+
+
 def make_pass_plan(stencil,
                    time_block: int = 1,
                    cells: Optional[int] = None,
-                   rows: int = 8) -> PassPlan:
+                   rows: int = 8,
+                   pack: Optional[bool] = None) -> PassPlan:
   """Plans one pass of ``time_block`` fused iterations.
 
   ``rows`` is only used by 3-D programs (tile height = warps per CTA).
@@ -312,7 +366,9 @@ def make_pass_plan(stencil,
                   lo_s=min(n.win_lo[s_dim] for n in outs),
                   max_lag=max(n.lag for n in outs),
                   rows=rows if dim == 3 else 1,
-                  align0=align0)
+                  align0=align0,
+                  pack=2 if (pack is not False and cells % 2 == 0 and
+                             packable(stencil)) else 1)
 
 
 def choose_time_block(stencil, requested: Optional[int] = None) -> int:

@@ -117,6 +117,57 @@ __device__ __forceinline__ T shfl_rel(T v) {
   }
 }
 
+// ---- packed fp32 pairs (Blackwell FADD2 / FMUL2) ------------------------------
+// Two IEEE fp32 values in one 64-bit register pair.  add/sub/mul round each
+// half to nearest-even exactly like the scalar instructions, so results are
+// bit-identical to scalar code; only the number of issue slots halves.
+struct F2 {
+  unsigned long long bits;
+};
+
+__device__ __forceinline__ F2 f2_pack(float lo, float hi) {
+  F2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.bits) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float f2_lo(F2 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v.bits));
+  return lo;
+}
+__device__ __forceinline__ float f2_hi(F2 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v.bits));
+  return hi;
+}
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+  F2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.bits) : "l"(a.bits), "l"(b.bits));
+  return r;
+}
+__device__ __forceinline__ F2 f2_sub(F2 a, F2 b) {
+  F2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.bits) : "l"(a.bits), "l"(b.bits));
+  return r;
+}
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+  F2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.bits) : "l"(a.bits), "l"(b.bits));
+  return r;
+}
+__device__ __forceinline__ F2 f2_neg(F2 a) {
+  F2 r;
+  r.bits = a.bits ^ 0x8000000080000000ull;
+  return r;
+}
+template <int kDelta>
+__device__ __forceinline__ F2 f2_shfl(F2 v) {
+  F2 r;
+  r.bits = kDelta > 0 ? __shfl_down_sync(kFullMask, v.bits, kDelta)
+                      : __shfl_up_sync(kFullMask, v.bits, -kDelta);
+  return r;
+}
+
 // warp-uniform OR of a per-lane flag
 __device__ __forceinline__ bool warp_any(bool flag) {
   return __any_sync(kFullMask, flag) != 0;

@@ -27,6 +27,8 @@
 // grid (store box).
 #pragma once
 
+#include <type_traits>
+
 #ifdef SODA_EMU
 #include <soda_emu.h>  // CPU emulation of the primitives below (tests only)
 #else
@@ -52,10 +54,85 @@ __host__ __device__ constexpr int floor_div(int a, int b) {
   return a >= 0 ? a / b : -((-a + b - 1) / b);
 }
 
+// ---- packed evaluation ----------------------------------------------------------
+// Programs whose tensors are all fp32 and whose statements only add, subtract
+// and multiply are evaluated two cells at a time (Prog::kPack == 2): a lane's
+// cells (2u, 2u+1) travel as one F2 register pair and every IR operation maps
+// to one FADD2 / FMUL2 instead of two FADD / FMUL.  Rounding is per element and
+// identical to the scalar instructions, so results do not change; the issue
+// slots of the arithmetic halve.  The generated functors are the same text in
+// both modes: they only use the operators and cast_to<> defined here.
+__device__ __forceinline__ F2 f2_splat(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ F2 operator+(F2 a, F2 b) { return f2_add(a, b); }
+__device__ __forceinline__ F2 operator-(F2 a, F2 b) { return f2_sub(a, b); }
+__device__ __forceinline__ F2 operator*(F2 a, F2 b) { return f2_mul(a, b); }
+__device__ __forceinline__ F2 operator-(F2 a) { return f2_neg(a); }
+__device__ __forceinline__ F2 operator+(F2 a) { return a; }
+// scalar operands are fp32 (or an int literal, which C++ converts to fp32 in a
+// float expression): broadcast to both halves
+template <typename S>
+__device__ __forceinline__ F2 operator+(F2 a, S b) { return f2_add(a, f2_splat(float(b))); }
+template <typename S>
+__device__ __forceinline__ F2 operator+(S a, F2 b) { return f2_add(f2_splat(float(a)), b); }
+template <typename S>
+__device__ __forceinline__ F2 operator-(F2 a, S b) { return f2_sub(a, f2_splat(float(b))); }
+template <typename S>
+__device__ __forceinline__ F2 operator-(S a, F2 b) { return f2_sub(f2_splat(float(a)), b); }
+template <typename S>
+__device__ __forceinline__ F2 operator*(F2 a, S b) { return f2_mul(a, f2_splat(float(b))); }
+template <typename S>
+__device__ __forceinline__ F2 operator*(S a, F2 b) { return f2_mul(f2_splat(float(a)), b); }
+
+template <typename To, typename From>
+__device__ __forceinline__ auto cast_to(From v) {
+  if constexpr (std::is_same<From, F2>::value) {
+    static_assert(std::is_same<To, float>::value, "packed values are fp32");
+    return v;
+  } else {
+    return To(v);
+  }
+}
+
+// A lane owns kCells cells = kUnits units of kPack cells.
+template <class Prog, int N>
+using UnitOf = typename std::conditional<Prog::kPack == 2, F2,
+                                         typename Prog::template T<N>>::type;
+template <class Prog>
+constexpr int kUnitsOf = Prog::kCells / Prog::kPack;
+
+template <class Prog, int N>
+__device__ __forceinline__ void units_from_cells(
+    UnitOf<Prog, N> (&units)[kUnitsOf<Prog>],
+    const typename Prog::template T<N> (&cells)[Prog::kCells]) {
+#pragma unroll
+  for (int u = 0; u < kUnitsOf<Prog>; ++u) {
+    if constexpr (Prog::kPack == 2) {
+      units[u] = f2_pack(cells[2 * u], cells[2 * u + 1]);
+    } else {
+      units[u] = cells[u];
+    }
+  }
+}
+
+template <class Prog, int N>
+__device__ __forceinline__ void cells_from_units(
+    typename Prog::template T<N> (&cells)[Prog::kCells],
+    const UnitOf<Prog, N> (&units)[kUnitsOf<Prog>]) {
+#pragma unroll
+  for (int u = 0; u < kUnitsOf<Prog>; ++u) {
+    if constexpr (Prog::kPack == 2) {
+      cells[2 * u] = f2_lo(units[u]);
+      cells[2 * u + 1] = f2_hi(units[u]);
+    } else {
+      cells[u] = units[u];
+    }
+  }
+}
+
 // ---- register sliding windows ------------------------------------------------
 template <class Prog, int N>
 struct RingStore : RingStore<Prog, N - 1> {
-  typename Prog::template T<N - 1> r[Prog::kNodes[N - 1].ring][Prog::kCells];
+  UnitOf<Prog, N - 1> r[Prog::kNodes[N - 1].ring][kUnitsOf<Prog>];
 };
 template <class Prog>
 struct RingStore<Prog, 0> {};
@@ -80,7 +157,13 @@ __device__ __forceinline__ void clear_rings(Rings<Prog>& rings) {
 #pragma unroll
     for (int s = 0; s < Prog::kNodes[N].ring; ++s) {
 #pragma unroll
-      for (int i = 0; i < Prog::kCells; ++i) r[s][i] = T(0);
+      for (int u = 0; u < kUnitsOf<Prog>; ++u) {
+        if constexpr (Prog::kPack == 2) {
+          r[s][u] = f2_splat(0.0f);
+        } else {
+          r[s][u] = T(0);
+        }
+      }
     }
     clear_rings<Prog, N + 1>(rings);
   }
@@ -95,17 +178,49 @@ __device__ __forceinline__ void advance_ring(Rings<Prog>& rings) {
 #pragma unroll
   for (int s = 0; s + 1 < Prog::kNodes[N].ring; ++s) {
 #pragma unroll
-    for (int i = 0; i < Prog::kCells; ++i) r[s][i] = r[s + 1][i];
+    for (int u = 0; u < kUnitsOf<Prog>; ++u) r[s][u] = r[s + 1][u];
   }
+}
+
+// The newest slice of node N as plain cells (for stores and exports).
+template <int N, class Prog>
+__device__ __forceinline__ void newest_cells(
+    const Rings<Prog>& rings,
+    typename Prog::template T<N> (&cells)[Prog::kCells]) {
+  cells_from_units<Prog, N>(
+      cells, ring_of<N, Prog>(rings)[Prog::kNodes[N].ring - 1]);
 }
 
 // ---- accessor handed to the generated functors --------------------------------
 // ld<K, DX, DY, DS>() is the value of the K-th loaded tensor of the statement
-// at offset (DX, DY, DS) from the cell being produced (DY is always 0 in 2-D;
-// DS is the offset in the streamed dimension).
+// at offset (DX, DY, DS) from the unit being produced (DY is always 0 in 2-D;
+// DS is the offset in the streamed dimension).  I is the unit index within the
+// lane.  Cells the lane does not own come from the neighbouring lanes by warp
+// shuffle; dimension-1 neighbours (3-D) from shared memory.
 template <class Prog, class Ctx, int N, int I>
 struct Access {
   const Ctx& ctx;
+
+  // one cell of producer P's slice in register slot kSlot, by cell index
+  // relative to the lane's first cell
+  template <int P, int kSlot, int kCell>
+  __device__ __forceinline__ typename Prog::template T<P> cell() const {
+    constexpr int kC = Prog::kCells;
+    constexpr int kLane = floor_div(kCell, kC);
+    constexpr int kLocal = kCell - kLane * kC;
+    typename Prog::template T<P> v;
+    if constexpr (Prog::kPack == 2) {
+      const F2 unit = ring_of<P, Prog>(ctx.rings)[kSlot][kLocal / 2];
+      v = (kLocal & 1) ? f2_hi(unit) : f2_lo(unit);
+    } else {
+      v = ring_of<P, Prog>(ctx.rings)[kSlot][kLocal];
+    }
+    if constexpr (kLane == 0) {
+      return v;
+    } else {
+      return shfl_rel<kLane>(v);
+    }
+  }
 
   template <int K, int DX, int DY, int DS>
   __device__ __forceinline__ auto ld() const {
@@ -113,35 +228,49 @@ struct Access {
     constexpr int P = Prog::kNodes[N].prod[K];
     constexpr int kDistance = Prog::kNodes[N].lag - Prog::kNodes[P].lag - DS;
     static_assert(kDistance >= 0, "plan: consumer runs ahead of its producer");
+    constexpr int kFirst = I * Prog::kPack + DX;  // first cell of the unit
     if constexpr (DY == 0) {
       constexpr int kSlot = Prog::kNodes[P].ring - 1 - kDistance;
       static_assert(kSlot >= 0, "plan: register window too short");
-      constexpr int kCol = I + DX;
-      constexpr int kLane = floor_div(kCol, Prog::kCells);
-      constexpr int kReg = kCol - kLane * Prog::kCells;
-      const auto v = ring_of<P, Prog>(ctx.rings)[kSlot][kReg];
-      if constexpr (kLane == 0) {
-        return v;
+      if constexpr (Prog::kPack == 1) {
+        return cell<P, kSlot, kFirst>();
+      } else if constexpr ((kFirst & 1) == 0) {
+        // an aligned pair: a whole unit of this or a neighbouring lane
+        constexpr int kUnit = floor_div(kFirst, 2);
+        constexpr int kLane = floor_div(kUnit, kUnitsOf<Prog>);
+        constexpr int kLocal = kUnit - kLane * kUnitsOf<Prog>;
+        const F2 v = ring_of<P, Prog>(ctx.rings)[kSlot][kLocal];
+        if constexpr (kLane == 0) {
+          return v;
+        } else {
+          return f2_shfl<kLane>(v);
+        }
       } else {
-        return shfl_rel<kLane>(v);
+        // a pair that straddles two units
+        return f2_pack(cell<P, kSlot, kFirst>(), cell<P, kSlot, kFirst + 1>());
       }
     } else {
       static_assert(Prog::kDim == 3, "dimension-1 offsets need a 3-D program");
       static_assert(kDistance < Prog::kNodes[P].smem_depth,
                     "plan: shared-memory window too short");
-      return ctx.template plane_load<P, kDistance, I + DX, DY>();
+      if constexpr (Prog::kPack == 1) {
+        return ctx.template plane_load<P, kDistance, kFirst, DY>();
+      } else {
+        return f2_pack(ctx.template plane_load<P, kDistance, kFirst, DY>(),
+                       ctx.template plane_load<P, kDistance, kFirst + 1, DY>());
+      }
     }
   }
 };
 
 template <class Prog, class Ctx, int N, int I = 0>
-__device__ __forceinline__ void eval_cells(Ctx& ctx) {
-  if constexpr (I < Prog::kCells) {
+__device__ __forceinline__ void eval_units(Ctx& ctx) {
+  if constexpr (I < kUnitsOf<Prog>) {
     using T = typename Prog::template T<N>;
     using F = typename Prog::template StageF<Prog::kNodes[N].src>;
     ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1][I] =
-        T(F::eval(Access<Prog, Ctx, N, I>{ctx}));
-    eval_cells<Prog, Ctx, N, I + 1>(ctx);
+        cast_to<T>(F::eval(Access<Prog, Ctx, N, I>{ctx}));
+    eval_units<Prog, Ctx, N, I + 1>(ctx);
   }
 }
 
@@ -292,9 +421,10 @@ template <class Prog, class Ctx, int N>
 __device__ __forceinline__ void store_node_2d(Ctx& ctx, int t) {
   using T = typename Prog::template T<N>;
   constexpr int kOut = Prog::kNodes[N].out;
-  store_slice<T, Prog::kCells>(
-      ctx.store[kOut], ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1],
-      t - Prog::kNodes[N].lag, ctx.any_partial);
+  T cells[Prog::kCells];
+  newest_cells<N, Prog>(ctx.rings, cells);
+  store_slice<T, Prog::kCells>(ctx.store[kOut], cells,
+                               t - Prog::kNodes[N].lag, ctx.any_partial);
 }
 
 // One step: every node of the pass DAG produces one row.  `r` is the row of
@@ -310,11 +440,12 @@ __device__ __forceinline__ void step_nodes_2d(Ctx& ctx, int t, int r) {
       const T* row = reinterpret_cast<const T*>(
           ctx.slot_base + S::template input_offset<M>() +
           r * S::template row_bytes<M>());
-      load_shared_vec<T, Prog::kCells>(
-          ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1],
-          row + ctx.lane * Prog::kCells);
+      T cells[Prog::kCells];
+      load_shared_vec<T, Prog::kCells>(cells, row + ctx.lane * Prog::kCells);
+      units_from_cells<Prog, N>(
+          ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1], cells);
     } else {
-      eval_cells<Prog, Ctx, N>(ctx);
+      eval_units<Prog, Ctx, N>(ctx);
     }
     if constexpr (Prog::kNodes[N].out >= 0) store_node_2d<Prog, Ctx, N>(ctx, t);
     step_nodes_2d<Prog, Ctx, N + 1>(ctx, t, r);
@@ -533,9 +664,10 @@ template <class Prog, class Ctx, int N>
 __device__ __forceinline__ void store_node_3d(Ctx& ctx, int t) {
   using T = typename Prog::template T<N>;
   constexpr int kOut = Prog::kNodes[N].out;
-  store_slice<T, Prog::kCells>(
-      ctx.store[kOut], ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1],
-      t - Prog::kNodes[N].lag, ctx.any_partial);
+  T cells[Prog::kCells];
+  newest_cells<N, Prog>(ctx.rings, cells);
+  store_slice<T, Prog::kCells>(ctx.store[kOut], cells,
+                               t - Prog::kNodes[N].lag, ctx.any_partial);
 }
 
 template <class Prog, class Ctx, int N = 0>
@@ -544,18 +676,21 @@ __device__ __forceinline__ void step_nodes_3d(Ctx& ctx, int t) {
     using T = typename Prog::template T<N>;
     constexpr int kC = Prog::kCells;
     advance_ring<N, Prog>(ctx.rings);
-    auto& newest = ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1];
     if constexpr (Prog::kNodes[N].kind == 0) {
-      load_shared_vec<T, kC>(newest,
-                             ctx.template plane<N, 0>() + ctx.cell_off);
+      T cells[kC];
+      load_shared_vec<T, kC>(cells, ctx.template plane<N, 0>() + ctx.cell_off);
+      units_from_cells<Prog, N>(
+          ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1], cells);
     } else {
-      eval_cells<Prog, Ctx, N>(ctx);
+      eval_units<Prog, Ctx, N>(ctx);
       if constexpr (Prog::kNodes[N].smem_depth > 0) {
         // export for the dimension-1 neighbours (read from the next step on)
         T* dst = const_cast<T*>(ctx.template plane<N, 0>()) + ctx.cell_off;
+        T cells[kC];
+        newest_cells<N, Prog>(ctx.rings, cells);
         Vec<T, kC> tmp;
 #pragma unroll
-        for (int i = 0; i < kC; ++i) tmp.v[i] = newest[i];
+        for (int i = 0; i < kC; ++i) tmp.v[i] = cells[i];
         *reinterpret_cast<Vec<T, kC>*>(dst) = tmp;
       }
     }

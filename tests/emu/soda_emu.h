@@ -300,6 +300,18 @@ inline int lane_id() { return threadIdx.x & 31; }
 inline void warp_sync() { soda_emu_cta->warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }
 inline void cta_sync() { soda_emu_cta->cta_barrier.arrive_and_wait(); }
 
+// packed fp32 pairs: two independent IEEE operations, as FADD2 / FMUL2 do
+struct F2 {
+  float lo, hi;
+};
+inline F2 f2_pack(float lo, float hi) { return F2{lo, hi}; }
+inline float f2_lo(F2 v) { return v.lo; }
+inline float f2_hi(F2 v) { return v.hi; }
+inline F2 f2_add(F2 a, F2 b) { return F2{a.lo + b.lo, a.hi + b.hi}; }
+inline F2 f2_sub(F2 a, F2 b) { return F2{a.lo - b.lo, a.hi - b.hi}; }
+inline F2 f2_mul(F2 a, F2 b) { return F2{a.lo * b.lo, a.hi * b.hi}; }
+inline F2 f2_neg(F2 a) { return F2{-a.lo, -a.hi}; }
+
 inline bool warp_any(bool flag) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto& slots = soda_emu_cta->warp_slots[warp];
@@ -327,6 +339,11 @@ inline T shfl_rel(T v) {
   if (src >= 0 && src < 32) memcpy(&result, &slots[src], sizeof(T));
   warp_sync();
   return result;
+}
+
+template <int kDelta>
+inline F2 f2_shfl(F2 v) {
+  return shfl_rel<kDelta>(v);
 }
 
 }  // namespace soda

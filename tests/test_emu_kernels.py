@@ -39,6 +39,8 @@ CASES_2D = [
     ('xcorr', dict()),
     ('jacobi2d', dict(extent=(3, 3))),
 ]
+CASES_2D.append(('jacobi2d', dict(extent=(300, 40), time_block=3, iterate=3,
+                                  options={'no_pack': True})))
 CASES_3D = [
     ('jacobi3d', dict(extent=(150, 21, 11), time_block=2, iterate=3,
                       options={'rows': 8}, segment=6)),

@@ -193,3 +193,13 @@ def test_pipelined_host_path_auto_chunks_large_grid():
   assert prog.launch_count() - before > prog.num_passes  # several chunks ran
   plain = prog.run_host({'t1': a}, opts=launcher.make_opts(host_chunks=1))['t0']
   assert np.array_equal(piped.view(np.uint32), plain.view(np.uint32))
+
+
+def test_packed_and_scalar_paths_agree():
+  """jacobi2d / heat3d use packed fp32 pairs (FADD2/FMUL2) by default; the
+  scalar path (--cuda-no-pack) must give the same bits."""
+  run_case('jacobi2d', extent=(1000, 700), seed=13, iterate=10, time_block=5)
+  run_case('jacobi2d', extent=(1000, 700), seed=13, iterate=10, time_block=5,
+           options={'no_pack': True})
+  run_case('heat3d', extent=(200, 40, 50), seed=13, iterate=4, time_block=2,
+           options={'no_pack': True})

@@ -84,3 +84,20 @@ def test_generated_source_contains_no_kernels():
   assert 'soda::NodeDesc kNodes' in text and 'struct Stage<0>' in text
   assert 'a.template ld<0, -1, 0, 0>()' in text
   assert 'extern "C" SODA_CUDA_API int soda_cuda_jacobi2d(' in text
+
+
+def test_packed_fp32_eligibility():
+  """Packed FADD2/FMUL2 evaluation: fp32 star stencils only."""
+  want = {'jacobi2d': True, 'jacobi3d': True, 'heat3d': True,
+          'seidel2d': False,   # nine loads, six at odd dimension-0 offsets
+          'blur': False, 'sobel2d': False, 'xcorr': False, 'erosion': False,
+          'denoise2d': False, 'denoise3d': False,   # sqrt, division
+          'contrast': False}
+  for name, flag in want.items():
+    assert plan.packable(common.stencil(name)) == flag, name
+  p = plan.make_pass_plan(common.stencil('jacobi2d'), time_block=2)
+  assert p.pack == 2
+  assert plan.make_pass_plan(common.stencil('jacobi2d'), time_block=2,
+                             pack=False).pack == 1
+  text = emit.emit_program(common.stencil('jacobi2d'))
+  assert 'kPack = 2' in text and 'soda::cast_to<float>' in text
