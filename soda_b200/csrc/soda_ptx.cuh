@@ -150,9 +150,19 @@ __device__ __forceinline__ F2 f2_sub(F2 a, F2 b) {
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.bits) : "l"(a.bits), "l"(b.bits));
   return r;
 }
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 whatever --fmad
+// says (it does not do that to the scalar .rn forms), which would change
+// results.  The product is therefore written as fma(a, b, -0.0) with the -0.0
+// read from constant memory at run time: a * b + (-0.0) rounds to exactly the
+// product (also for +-0 products), ptxas cannot fold an addend it does not
+// know, and the FFMA2 cannot absorb a second add.
+__constant__ unsigned long long soda_neg_zero_pair = 0x8000000080000000ull;
+
 __device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
   F2 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.bits) : "l"(a.bits), "l"(b.bits));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(r.bits)
+      : "l"(a.bits), "l"(b.bits), "l"(soda_neg_zero_pair));
   return r;
 }
 __device__ __forceinline__ F2 f2_neg(F2 a) {

@@ -54,6 +54,17 @@ def test_library_is_sm_100a_with_tma(library):
   assert 'STG.E.128' in sass        # vectorised stores
 
 
+def test_packed_products_cannot_be_contracted(library):
+  """ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 regardless of
+  --fmad (seen with CUDA 12.9), which would change results; the packed multiply
+  is therefore an FFMA2 with a run-time -0.0 addend and no FMUL2 may remain."""
+  sass = subprocess.run(['cuobjdump', '-sass', library], capture_output=True,
+                        text=True).stdout
+  assert 'FADD2' in sass and 'FFMA2' in sass   # jacobi2d uses the packed path
+  assert 'FMUL2' not in sass
+  assert ' FFMA ' not in sass and ' FFMA.' not in sass   # --fmad=false holds
+
+
 def test_program_info_without_gpu(library):
   prog = launcher.CudaProgram(library)
   assert (prog.app_name, prog.dim, prog.iterate) == ('jacobi2d', 2, 2)

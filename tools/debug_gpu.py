@@ -42,3 +42,24 @@ elif which == 'dev':
     plan.run_device([d_in.data_ptr()], [(16384, 0)], [d_out.data_ptr()], [(16384, 0)])
     torch.cuda.synchronize()
     print('OK dev', flush=True)
+if which == 'crseidel':
+    for opts in ({'no_pack': True}, None):
+        try:
+            case('seidel2d', (500, 200), options=opts, computation_reuse='yes')
+        except AssertionError as e:
+            print('FAIL', opts, str(e)[:200])
+    # same arithmetic shape without CR: 3-term sum times .1111111f
+    import tempfile
+    from soda_b200 import sodac as _s
+    src = common.source('jacobi2d').replace('0.2f', '.1111111f')
+    st = _s.compile_source(src)
+    for opts in ({'no_pack': True}, None):
+        prog = cb.compile_stencil(st, options=opts)
+        ins = common.make_inputs(st, (500, 200), seed=1)
+        out = prog.run_host(ins)
+        want = common.oracle_outputs(st, ins)
+        try:
+            common.assert_matches_oracle(st, (500, 200), out, want)
+            print('OK jacobi .1111111f', opts)
+        except AssertionError as e:
+            print('FAIL jacobi .1111111f', opts, str(e)[:200])
