@@ -241,7 +241,11 @@ def emit_program(stencil,
       tb: planner.make_pass_plan(stencil,
                                  time_block=tb,
                                  cells=options.get('cells'),
-                                 rows=options.get('rows') or 8,
+                                 # measured on B200 (512^3 jacobi3d/heat3d):
+                                 # 8-row tiles are best without temporal
+                                 # blocking, 32-row tiles with it (halo share)
+                                 rows=options.get('rows') or (8 if tb == 1
+                                                              else 32),
                                  pack=False if options.get('no_pack') else None)
       for tb in variants
   }
