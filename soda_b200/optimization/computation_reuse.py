@@ -30,8 +30,11 @@ computation-reuse schedule becomes reuse of shared partial sums").
 """
 import collections
 import itertools
+import json
 import logging
-from typing import Dict, FrozenSet, List, Optional, Sequence, Tuple
+import os
+import subprocess
+from typing import Dict, FrozenSet, Iterator, List, Optional, Sequence, Tuple
 
 from soda_b200 import ir, mutator, util, visitor
 
@@ -42,6 +45,94 @@ Leaf = Tuple[Index, int]  # (relative index, absolute attribute tag)
 
 METHODS = ('yes', 'greedy', 'optimal', 'glore', 'beam', 'built-in',
            'built-in:greedy', 'built-in:optimal')
+
+
+NATIVE_SOURCE = os.path.join(
+    os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'csrc',
+    'soda_cr', 'soda_cr.cpp')
+NATIVE_BINARY = os.path.join(os.path.dirname(NATIVE_SOURCE), 'soda-cr')
+
+
+def build_native(force: bool = False) -> Optional[str]:
+  """Compiles the native scheduler (csrc/soda_cr/soda_cr.cpp) with g++."""
+  if os.path.exists(NATIVE_BINARY) and not force and \
+      os.path.getmtime(NATIVE_BINARY) >= os.path.getmtime(NATIVE_SOURCE):
+    return NATIVE_BINARY
+  tmp = '%s.%d.tmp' % (NATIVE_BINARY, os.getpid())
+  result = subprocess.run(
+      ['g++', '-O2', '-std=c++17', '-o', tmp, NATIVE_SOURCE],
+      capture_output=True, text=True)
+  if result.returncode != 0:
+    _logger.warning('cannot build soda-cr: %s', result.stderr)
+    return None
+  os.replace(tmp, NATIVE_BINARY)
+  return NATIVE_BINARY
+
+
+class Linearizer:
+  """Maps index tuples to integers such that differences of integers identify
+  differences of tuples: dimension d gets ``2 * extent_d - 1`` slots (or the
+  tile size, for all but the last dimension).  Same contract as the
+  reference's (reference :72-154, pinned by
+  src/tests/optimization/test_computation_reuse.py:33-42)."""
+
+  def __init__(self, rattrs: Sequence[Sequence[int]],
+               tile_size: Sequence[int] = ()):
+    num_dim = len(rattrs[0])
+    self.maxs = [max(r[d] for r in rattrs) for d in range(num_dim)]
+    self.mins = [min(r[d] for r in rattrs) for d in range(num_dim)]
+    if tile_size:
+      self.sizes = tuple(tile_size)[:-1] + (
+          (self.maxs[-1] - self.mins[-1] + 1) * 2 - 1,)
+    else:
+      self.sizes = tuple((self.maxs[d] - self.mins[d] + 1) * 2 - 1
+                         for d in range(num_dim))
+
+  @property
+  def num_dim(self) -> int:
+    return len(self.maxs)
+
+  @property
+  def dims(self) -> Tuple[int, ...]:
+    return tuple(range(self.num_dim))
+
+  @property
+  def weights(self) -> List[int]:
+    weights = [1] * self.num_dim
+    for d in self.dims[1:]:
+      weights[d] = weights[d - 1] * self.sizes[d - 1]
+    return weights
+
+  def apply(self, rattr: Sequence[int]) -> int:
+    return sum((value - low) * weight
+               for value, weight, low in zip(rattr, self.weights, self.mins))
+
+  def restore(self, rattr: int) -> Tuple[int, ...]:
+    restored = []
+    for d in reversed(self.dims):
+      value = rattr // self.weights[d]
+      rattr -= value * self.weights[d]
+      restored.append(self.mins[d] + value)
+    return tuple(reversed(restored))
+
+  def __call__(self, rattr):
+    if isinstance(rattr, int):
+      return self.restore(rattr)
+    return self.apply(rattr)
+
+
+def range_from_middle(n: int) -> Iterator[int]:
+  """0..n-1 from the middle outwards (reference :157-174)."""
+  middle = n // 2
+  if n % 2:
+    yield middle
+    for shift in range(1, middle + 1):
+      yield middle - shift
+      yield middle + shift
+  else:
+    for shift in range(middle):
+      yield middle - shift - 1
+      yield middle + shift
 
 
 def _sub(a: Index, b: Index) -> Index:
@@ -241,9 +332,54 @@ def total_distance(tree: Pattern) -> int:
   return total
 
 
+def find_schedule_native(leaves: Sequence[Leaf],
+                         flag: Optional[str] = None) -> Optional[Pattern]:
+  """Runs the native scheduler (csrc/soda_cr) over the reference's JSON
+  contract (reference :1692-1743) and rebuilds the schedule as a Pattern tree.
+  Returns None if the binary is unavailable or its answer does not cover the
+  operands exactly."""
+  if not os.path.exists(NATIVE_BINARY):
+    return None
+  linearizer = Linearizer([idx for idx, _ in leaves])
+  request = {
+      'rattrs': [linearizer.apply(idx) for idx, _ in leaves],
+      'aattrs': [tag for _, tag in leaves],
+      'linearizer': {'mins': linearizer.mins, 'maxs': linearizer.maxs,
+                     'sizes': list(linearizer.sizes)},
+  }
+  try:
+    result = subprocess.run([NATIVE_BINARY] + ([flag] if flag else []),
+                            input=json.dumps(request), capture_output=True,
+                            text=True, check=True, timeout=300)
+    answer = json.loads(result.stdout)
+  except (OSError, subprocess.SubprocessError, ValueError) as e:
+    _logger.warning('soda-cr failed: %s', e)
+    return None
+  dim = len(leaves[0][0])
+
+  def build(node, offset: int) -> Pattern:
+    if not isinstance(node, dict):
+      return leaf_pattern(int(node), dim)
+    left = build(node['left'], offset)
+    right_offset = offset + int(node['distance'])
+    right = build(node['right'], right_offset)
+    return merge(left, right, _sub(linearizer.restore(right_offset),
+                                   linearizer.restore(offset)))
+
+  tree = build(answer, min(request['rattrs']))
+  base = min((idx for idx, _ in leaves), key=_order)
+  expected = frozenset((_sub(idx, base), tag) for idx, tag in leaves)
+  if tree.leaves != expected:
+    _logger.warning('soda-cr returned a schedule that does not cover the '
+                    'operands; falling back to the built-in search')
+    return None
+  return tree
+
+
 def find_schedule(leaves: Sequence[Leaf], beam_width: int = 6,
                   branch: int = 4) -> Pattern:
-  """Best schedule found for the reduction over ``leaves``."""
+  """Best schedule found for the reduction over ``leaves`` by the built-in
+  (Python) beam search."""
   dim = len(leaves[0][0])
   start: List[Item] = [(idx, leaf_pattern(tag, dim)) for idx, tag in leaves]
   if len(leaves) <= 7:
@@ -412,7 +548,15 @@ def computation_reuse(stencil):
         expression = Expression(obj, stencil.dim)
       except CannotHandle:
         return obj
-      tree = find_schedule(expression.leaves)
+      # like the reference (:1840-1856): the external tool when it exists and
+      # the method does not ask for the built-in search, else the built-in one
+      tree = None
+      if not method.startswith('built-in'):
+        flag = {'greedy': '--greedy', 'optimal': '--brute-force',
+                'beam': '--beam'}.get(method)
+        tree = find_schedule_native(expression.leaves, flag)
+      if tree is None:
+        tree = find_schedule(expression.leaves)
       if tree.num_ops >= len(expression.leaves) - 1:
         return obj  # nothing gained
       _logger.info('%s: %d operations instead of %d: %s', stmt.name,

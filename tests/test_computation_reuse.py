@@ -17,6 +17,61 @@ def ops(rattrs, aattrs=None):
   return cr.find_schedule(list(zip(rattrs, aattrs))).num_ops
 
 
+def test_range_from_middle():
+  assert tuple(cr.range_from_middle(3)) == (1, 0, 2)
+  assert tuple(cr.range_from_middle(4)) == (1, 2, 0, 3)
+  assert tuple(cr.range_from_middle(5)) == (2, 1, 3, 0, 4)
+  assert tuple(cr.range_from_middle(6)) == (2, 3, 1, 4, 0, 5)
+  for n in range(100):
+    assert sorted(cr.range_from_middle(n)) == list(range(n))
+
+
+def test_3x3_linearizer():
+  rattrs = ((-1, -1), (-1, 0), (-1, 1), (-1, 0), (0, 0), (1, 0), (-1, 1),
+            (0, 1), (1, 1))
+  linearizer = cr.Linearizer(rattrs)
+  assert linearizer.num_dim == 2
+  assert list(linearizer.maxs) == [1, 1] and list(linearizer.mins) == [-1, -1]
+  assert list(linearizer.weights) == [1, 5]
+  assert [tuple(linearizer(linearizer(r))) for r in rattrs] == list(rattrs)
+
+
+def native_ops(rattrs, aattrs=None, flag=None):
+  assert cr.build_native() is not None
+  aattrs = aattrs or [0] * len(rattrs)
+  tree = cr.find_schedule_native(list(zip(rattrs, aattrs)), flag)
+  assert tree is not None
+  return tree.num_ops
+
+
+def test_native_scheduler_matches_pinned_costs():
+  """The C++ soda-cr (csrc/soda_cr) behind the reference's JSON contract."""
+  grid = lambda m, n: [(x, y) for y in range(n) for x in range(m)]
+  assert native_ops([(1, 0), (0, 1), (1, 1), (2, 1), (1, 2)]) == 3  # jacobi2d
+  assert native_ops(grid(3, 3)) == 4
+  assert native_ops(grid(5, 5)) == 6
+  assert native_ops(grid(11, 11)) == 10
+  assert native_ops(grid(16, 16)) == 8
+  for aattrs, want in CASES_3X3[1:]:
+    assert native_ops(grid(3, 3), list(aattrs)) <= want
+  assert native_ops(grid(3, 2), [1, 1, 1, 1, 3, 1]) == 4
+  assert native_ops(grid(5, 5), flag='--greedy') <= 8
+
+
+def test_native_scheduler_json_contract():
+  import json
+  import subprocess
+  assert cr.build_native() is not None
+  request = {'rattrs': [0, 1, 2, 3], 'aattrs': [1, 2, 1, 2], 'num_pruned': 64}
+  out = json.loads(subprocess.run([cr.NATIVE_BINARY], input=json.dumps(request),
+                                  capture_output=True, text=True,
+                                  check=True).stdout)
+  # y[0] = x[0] + 2 x[1];  y[0] + y[2]   (reference test_simple_cr)
+  assert out['num_ops'] == 2 and out['distance'] == 2
+  assert out['left'] == {'left': 1, 'right': 2, 'distance': 1} == out['right']
+  assert out['rattrs'] == [0, 1, 2, 3]
+
+
 def test_simple_cr():
   # x[0] + 2 x[1] + x[2] + 2 x[3]  ->  y[0] = x[0] + 2 x[1];  y[0] + y[2]
   assert ops((0, 1, 2, 3), (1, 2, 1, 2)) == 2
