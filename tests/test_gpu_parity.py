@@ -203,3 +203,21 @@ def test_packed_and_scalar_paths_agree():
            options={'no_pack': True})
   run_case('heat3d', extent=(200, 40, 50), seed=13, iterate=4, time_block=2,
            options={'no_pack': True})
+
+
+def test_fast_fp_mode_tolerance():
+  """--cuda-fast-fp lets ptxas contract a*b+c into FMA.  BASELINE north star:
+  "<= 2 ulp per step"; it must also pass the reference's own criterion
+  (abs or rel error <= 1e-5, src/soda/codegen/frt/host.py:633-649)."""
+  from oracle import compare
+  st = common.stencil('heat3d', iterate=4)
+  prog = cuda_backend.compile_stencil(st, time_block=2,
+                                      options={'fast_fp': True})
+  assert prog.info.strict_fp == 0
+  extent = (200, 40, 50)
+  inputs = common.make_inputs(st, extent, seed=21)
+  got = prog.run_host(inputs)['out']
+  want = common.oracle_outputs(st, inputs)['out']
+  inside = common.box_index(st.valid_box('out', extent))
+  assert compare.error_count(got[inside], want[inside]) == 0
+  assert compare.ulp_distance(got[inside], want[inside]).max() <= 2 * st.iterate

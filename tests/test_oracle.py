@@ -136,3 +136,20 @@ def test_default_extents_match_reference_main():
           'seidel2d': (32, 6), 'sobel2d': (32, 4), 'xcorr': (480, 20)}
   for name, extent in want.items():
     assert golden.default_extent(common.stencil(name)) == extent
+
+
+def test_reference_compare_criterion():
+  """src/soda/codegen/frt/host.py:633-657: ints exact; floats fail only when
+  both the absolute and the relative error exceed 1e-5."""
+  from oracle import compare
+  want = np.array([1.0, 1000.0, 1e-7, 0.0], dtype=np.float32)
+  got = want + np.array([5e-6, 5e-3, 5e-6, 2e-5], dtype=np.float32)
+  # 5e-6 abs ok; 5e-3 on 1000 is 5e-6 relative ok; 5e-6 abs ok; 2e-5 on 0: fail
+  assert compare.error_count(got, want) == 1
+  assert compare.error_count(got, want, threshold=0) == 4
+  ints = np.array([1, 2, 3], dtype=np.int16)
+  assert compare.error_count(ints, ints) == 0
+  assert compare.error_count(ints, ints + np.int16(1)) == 3
+  a = np.float32(1.0)
+  b = np.nextafter(a, np.float32(2.0))
+  assert compare.ulp_distance(np.array([a]), np.array([b]))[0] == 1
