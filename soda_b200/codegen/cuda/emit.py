@@ -179,6 +179,7 @@ def _emit_pass(ns: str, stencil, pass_plan: planner.PassPlan,
       'kValid0': pass_plan.valid[0],
       'kAlign0': pass_plan.align0,
       'kPack': pass_plan.pack,
+      'kSkew': pass_plan.skew,
       'kLoS': pass_plan.lo_s,
       'kMaxLag': pass_plan.max_lag,
   }
@@ -246,7 +247,9 @@ def emit_program(stencil,
                                  # blocking, 32-row tiles with it (halo share)
                                  rows=options.get('rows') or (8 if tb == 1
                                                               else 32),
-                                 pack=False if options.get('no_pack') else None)
+                                 pack=False if options.get('no_pack') else None,
+                                 pipelined=False
+                                 if options.get('no_pipeline') else None)
       for tb in variants
   }
   stages = plans[variants[0]].stages

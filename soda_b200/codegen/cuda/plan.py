@@ -84,6 +84,9 @@ class PassPlan:
   rows: int = 1  # 3-D: tile rows (= warps per CTA)
   align0: int = 1  # strip origins are multiples of this many cells
   pack: int = 1  # cells evaluated per instruction (2: packed fp32 pairs)
+  # 1: every node reads what its producers had produced *before* the current
+  # step (software pipelining across the DAG), 0: producers run first
+  skew: int = 0
 
   @property
   def output_nodes(self) -> List[Node]:
@@ -144,10 +147,12 @@ def default_cells(stencil) -> int:
 
 def packable(stencil) -> bool:
   """Whether the program can be evaluated two cells at a time with packed fp32
-  instructions (FADD2 / FMUL2): every tensor is ``float`` and every statement
+  instructions (FADD2 / FFMA2): every tensor is ``float`` and every statement
   only adds, subtracts and multiplies loads, fp32 literals and integer
   literals.  Anything else (division, calls, comparisons, double literals,
-  integer tensors) keeps the scalar path."""
+  integer tensors) keeps the scalar path.  A pair holds cells ``(u, u + C/2)``
+  of a lane, so dimension-0 offsets cost one shuffle and one move per lane
+  boundary crossed, whatever their parity (soda_stream.cuh)."""
   float_t = ir.Type('float')
   types = stencil.input_types + stencil.output_types + tuple(
       stencil.local_types)
@@ -180,17 +185,6 @@ def packable(stencil) -> bool:
         return False
     if not ok(stmt.expr):
       return False
-    # a load at an odd dimension-0 offset straddles two register pairs and
-    # costs moves to assemble; measured on B200 the packed path only pays off
-    # while there are at most two of them per statement (5/7-point stars:
-    # +9 % at time block 5-6; 9-point box: -8 %)
-    odd = {
-        tuple(a - b for a, b in zip(ref.idx, stmt.ref.idx))
-        for ref in _stmt_loads(stmt)
-        if (ref.idx[0] - stmt.ref.idx[0]) % 2
-    }
-    if len(odd) > 2:
-      return False
   return True
 
 
@@ -198,10 +192,18 @@ def make_pass_plan(stencil,
                    time_block: int = 1,
                    cells: Optional[int] = None,
                    rows: int = 8,
-                   pack: Optional[bool] = None) -> PassPlan:
+                   pack: Optional[bool] = None,
+                   pipelined: Optional[bool] = None) -> PassPlan:
   """Plans one pass of ``time_block`` fused iterations.
 
   ``rows`` is only used by 3-D programs (tile height = warps per CTA).
+
+  ``pipelined`` (2-D, default on): node ``n`` only reads slices its producers
+  finished in an earlier step, so the nodes of one step do not depend on each
+  other and the ``time_block`` dependent chains of a step (5 additions each in
+  jacobi2d) overlap instead of running back to back.  Costs one step of lag
+  per DAG level and no registers: a window of depth ``d`` still holds the
+  ``d`` slices a consumer reads, they are just one step older.
   """
   if stencil.param_stmts:
     raise util.SemanticError('param statements are not supported by the CUDA '
@@ -220,6 +222,11 @@ def make_pass_plan(stencil,
     if not t.is_executable:
       raise util.SemanticError('type %s is not supported by the CUDA backend' %
                                t)
+  if pipelined is None:
+    pipelined = dim == 2
+  if pipelined and dim != 2:
+    raise util.SemanticError('the pipelined schedule is a 2-D feature')
+  step_skew = 1 if pipelined else 0
   cells = cells or default_cells(stencil)
   strip = WARP * cells
   stages = stage_descs(stencil)
@@ -288,7 +295,7 @@ def make_pass_plan(stencil,
     for prod_id, deltas in zip(node.prods, node.deltas):
       prod = nodes[prod_id]
       for delta in deltas:
-        skew = 0
+        skew = step_skew
         if dim == 3 and delta[1] != 0 and prod.kind != 'input':
           # dimension-1 neighbours come from shared memory written by other
           # warps in an earlier step: read one step late, one barrier per step
@@ -320,10 +327,12 @@ def make_pass_plan(stencil,
           distance = consumer.lag - node.lag - delta[s_dim]
           if distance < 0:
             raise util.InternalError('negative reuse distance')
+          if distance < step_skew:
+            raise util.InternalError('consumer not behind its producer')
           if dim == 3 and delta[1] != 0:
             smem_depth = max(smem_depth, distance + 1)
           else:
-            ring = max(ring, distance + 1)
+            ring = max(ring, distance + 1 - step_skew)
     node.ring = ring
     node.smem_depth = smem_depth
 
@@ -368,7 +377,8 @@ def make_pass_plan(stencil,
                   rows=rows if dim == 3 else 1,
                   align0=align0,
                   pack=2 if (pack is not False and cells % 2 == 0 and
-                             packable(stencil)) else 1)
+                             packable(stencil)) else 1,
+                  skew=step_skew)
 
 
 def choose_time_block(stencil, requested: Optional[int] = None) -> int:

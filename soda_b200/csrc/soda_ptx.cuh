@@ -165,6 +165,18 @@ __device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
       : "l"(a.bits), "l"(b.bits), "l"(soda_neg_zero_pair));
   return r;
 }
+// A pair assembled from two registers that were loaded as part of a wider
+// vector (LDS.128) is only a register copy to ptxas, which then re-assembles it
+// with two MOVs at every use.  Adding a zero that is only known at run time
+// makes each half a value in its own right, produced once, directly in place.
+__constant__ int soda_zero_word = 0;
+
+__device__ __forceinline__ F2 f2_pack_once(float lo, float hi) {
+  const int z = soda_zero_word;
+  return f2_pack(__int_as_float(__float_as_int(lo) + z),
+                 __int_as_float(__float_as_int(hi) + z));
+}
+
 __device__ __forceinline__ F2 f2_neg(F2 a) {
   F2 r;
   r.bits = a.bits ^ 0x8000000080000000ull;

@@ -56,12 +56,22 @@ __host__ __device__ constexpr int floor_div(int a, int b) {
 
 // ---- packed evaluation ----------------------------------------------------------
 // Programs whose tensors are all fp32 and whose statements only add, subtract
-// and multiply are evaluated two cells at a time (Prog::kPack == 2): a lane's
-// cells (2u, 2u+1) travel as one F2 register pair and every IR operation maps
-// to one FADD2 / FMUL2 instead of two FADD / FMUL.  Rounding is per element and
-// identical to the scalar instructions, so results do not change; the issue
-// slots of the arithmetic halve.  The generated functors are the same text in
-// both modes: they only use the operators and cast_to<> defined here.
+// and multiply are evaluated two cells at a time (Prog::kPack == 2): every IR
+// operation maps to one FADD2 / FFMA2 instead of two FADD / FMUL.  Rounding is
+// per element and identical to the scalar instructions, so results do not
+// change; the issue slots of the arithmetic halve.  The generated functors are
+// the same text in both modes: they only use the operators and cast_to<>
+// defined here.
+//
+// Pair layout ("half split"): with kCells = 2H cells per lane, unit u holds the
+// lane's cells (u, u + H) - not two adjacent cells.  A load at dimension-0
+// offset dx of unit u then is
+//   * unit u + dx itself while 0 <= u + dx < H (no instruction at all), or
+//   * a unit rotated across the lane boundary, (hi of unit j, lo of unit j of
+//     the next lane): one 32-bit shuffle and one register move,
+// whereas adjacent-cell pairs need two moves for every odd dx of every unit
+// (measured on the jacobi2d time-block-5 kernel: 7.4 MOV per 10 packed
+// arithmetic instructions before, 2 after).
 __device__ __forceinline__ F2 f2_splat(float v) { return f2_pack(v, v); }
 __device__ __forceinline__ F2 operator+(F2 a, F2 b) { return f2_add(a, b); }
 __device__ __forceinline__ F2 operator-(F2 a, F2 b) { return f2_sub(a, b); }
@@ -107,7 +117,7 @@ __device__ __forceinline__ void units_from_cells(
 #pragma unroll
   for (int u = 0; u < kUnitsOf<Prog>; ++u) {
     if constexpr (Prog::kPack == 2) {
-      units[u] = f2_pack(cells[2 * u], cells[2 * u + 1]);
+      units[u] = f2_pack_once(cells[u], cells[u + kUnitsOf<Prog>]);
     } else {
       units[u] = cells[u];
     }
@@ -121,8 +131,8 @@ __device__ __forceinline__ void cells_from_units(
 #pragma unroll
   for (int u = 0; u < kUnitsOf<Prog>; ++u) {
     if constexpr (Prog::kPack == 2) {
-      cells[2 * u] = f2_lo(units[u]);
-      cells[2 * u + 1] = f2_hi(units[u]);
+      cells[u] = f2_lo(units[u]);
+      cells[u + kUnitsOf<Prog>] = f2_hi(units[u]);
     } else {
       cells[u] = units[u];
     }
@@ -210,8 +220,9 @@ struct Access {
     constexpr int kLocal = kCell - kLane * kC;
     typename Prog::template T<P> v;
     if constexpr (Prog::kPack == 2) {
-      const F2 unit = ring_of<P, Prog>(ctx.rings)[kSlot][kLocal / 2];
-      v = (kLocal & 1) ? f2_hi(unit) : f2_lo(unit);
+      constexpr int kH = kUnitsOf<Prog>;
+      const F2 unit = ring_of<P, Prog>(ctx.rings)[kSlot][kLocal % kH];
+      v = kLocal >= kH ? f2_hi(unit) : f2_lo(unit);
     } else {
       v = ring_of<P, Prog>(ctx.rings)[kSlot][kLocal];
     }
@@ -227,27 +238,40 @@ struct Access {
     static_assert(K < Prog::kNodes[N].nprod, "functor loads an undeclared slot");
     constexpr int P = Prog::kNodes[N].prod[K];
     constexpr int kDistance = Prog::kNodes[N].lag - Prog::kNodes[P].lag - DS;
-    static_assert(kDistance >= 0, "plan: consumer runs ahead of its producer");
-    constexpr int kFirst = I * Prog::kPack + DX;  // first cell of the unit
+    static_assert(kDistance >= Prog::kSkew,
+                  "plan: consumer runs ahead of its producer");
+    // first cell of the unit, relative to the lane's first cell (packed: the
+    // second one is kHalf cells further)
+    constexpr int kFirst = I + DX;
+    constexpr int kHalf = kUnitsOf<Prog>;
     if constexpr (DY == 0) {
-      constexpr int kSlot = Prog::kNodes[P].ring - 1 - kDistance;
+      // pipelined plans (kSkew == 1) evaluate a node before its producers
+      // advance in the same step: their newest slice is one step old
+      constexpr int kSlot = Prog::kNodes[P].ring - 1 - (kDistance - Prog::kSkew);
       static_assert(kSlot >= 0, "plan: register window too short");
       if constexpr (Prog::kPack == 1) {
         return cell<P, kSlot, kFirst>();
-      } else if constexpr ((kFirst & 1) == 0) {
-        // an aligned pair: a whole unit of this or a neighbouring lane
-        constexpr int kUnit = floor_div(kFirst, 2);
-        constexpr int kLane = floor_div(kUnit, kUnitsOf<Prog>);
-        constexpr int kLocal = kUnit - kLane * kUnitsOf<Prog>;
-        const F2 v = ring_of<P, Prog>(ctx.rings)[kSlot][kLocal];
-        if constexpr (kLane == 0) {
-          return v;
-        } else {
-          return f2_shfl<kLane>(v);
-        }
       } else {
-        // a pair that straddles two units
-        return f2_pack(cell<P, kSlot, kFirst>(), cell<P, kSlot, kFirst + 1>());
+        constexpr int kLane = floor_div(kFirst, Prog::kCells);
+        constexpr int kLocal = kFirst - kLane * Prog::kCells;
+        if constexpr (kLocal < kHalf) {
+          // a whole unit of this or a neighbouring lane
+          const F2 v = ring_of<P, Prog>(ctx.rings)[kSlot][kLocal];
+          if constexpr (kLane == 0) {
+            return v;
+          } else {
+            return f2_shfl<kLane>(v);
+          }
+        } else {
+          // rotated across a lane boundary: (hi of unit j in lane kLane,
+          // lo of unit j in lane kLane + 1)
+          const F2 v = ring_of<P, Prog>(ctx.rings)[kSlot][kLocal - kHalf];
+          float first = f2_hi(v);
+          float second = f2_lo(v);
+          if constexpr (kLane != 0) first = shfl_rel<kLane>(first);
+          if constexpr (kLane + 1 != 0) second = shfl_rel<kLane + 1>(second);
+          return f2_pack(first, second);
+        }
       }
     } else {
       static_assert(Prog::kDim == 3, "dimension-1 offsets need a 3-D program");
@@ -256,8 +280,9 @@ struct Access {
       if constexpr (Prog::kPack == 1) {
         return ctx.template plane_load<P, kDistance, kFirst, DY>();
       } else {
-        return f2_pack(ctx.template plane_load<P, kDistance, kFirst, DY>(),
-                       ctx.template plane_load<P, kDistance, kFirst + 1, DY>());
+        return f2_pack(
+            ctx.template plane_load<P, kDistance, kFirst, DY>(),
+            ctx.template plane_load<P, kDistance, kFirst + kHalf, DY>());
       }
     }
   }
@@ -429,26 +454,36 @@ __device__ __forceinline__ void store_node_2d(Ctx& ctx, int t) {
 
 // One step: every node of the pass DAG produces one row.  `r` is the row of
 // the current chunk that holds input row t.
-template <class Prog, class Ctx, int N = 0>
+template <class Prog, class Ctx, int N>
+__device__ __forceinline__ void step_node_2d(Ctx& ctx, int t, int r) {
+  using T = typename Prog::template T<N>;
+  advance_ring<N, Prog>(ctx.rings);
+  if constexpr (Prog::kNodes[N].kind == 0) {
+    constexpr int M = Prog::kNodes[N].src;
+    using S = Smem2D<Prog>;
+    const T* row = reinterpret_cast<const T*>(
+        ctx.slot_base + S::template input_offset<M>() +
+        r * S::template row_bytes<M>());
+    T cells[Prog::kCells];
+    load_shared_vec<T, Prog::kCells>(cells, row + ctx.lane * Prog::kCells);
+    units_from_cells<Prog, N>(
+        ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1], cells);
+  } else {
+    eval_units<Prog, Ctx, N>(ctx);
+  }
+  if constexpr (Prog::kNodes[N].out >= 0) store_node_2d<Prog, Ctx, N>(ctx, t);
+}
+
+// Producers first (kSkew == 0), or consumers first (kSkew == 1, pipelined
+// plans): every node then reads only what earlier steps left in the windows,
+// the nodes of a step are independent of each other and their dependent
+// instruction chains overlap.
+template <class Prog, class Ctx, int K = 0>
 __device__ __forceinline__ void step_nodes_2d(Ctx& ctx, int t, int r) {
-  if constexpr (N < Prog::kNumNodes) {
-    using T = typename Prog::template T<N>;
-    advance_ring<N, Prog>(ctx.rings);
-    if constexpr (Prog::kNodes[N].kind == 0) {
-      constexpr int M = Prog::kNodes[N].src;
-      using S = Smem2D<Prog>;
-      const T* row = reinterpret_cast<const T*>(
-          ctx.slot_base + S::template input_offset<M>() +
-          r * S::template row_bytes<M>());
-      T cells[Prog::kCells];
-      load_shared_vec<T, Prog::kCells>(cells, row + ctx.lane * Prog::kCells);
-      units_from_cells<Prog, N>(
-          ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1], cells);
-    } else {
-      eval_units<Prog, Ctx, N>(ctx);
-    }
-    if constexpr (Prog::kNodes[N].out >= 0) store_node_2d<Prog, Ctx, N>(ctx, t);
-    step_nodes_2d<Prog, Ctx, N + 1>(ctx, t, r);
+  if constexpr (K < Prog::kNumNodes) {
+    constexpr int N = Prog::kSkew ? Prog::kNumNodes - 1 - K : K;
+    step_node_2d<Prog, Ctx, N>(ctx, t, r);
+    step_nodes_2d<Prog, Ctx, K + 1>(ctx, t, r);
   }
 }
 

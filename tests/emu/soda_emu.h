@@ -305,6 +305,7 @@ struct F2 {
   float lo, hi;
 };
 inline F2 f2_pack(float lo, float hi) { return F2{lo, hi}; }
+inline F2 f2_pack_once(float lo, float hi) { return F2{lo, hi}; }
 inline float f2_lo(F2 v) { return v.lo; }
 inline float f2_hi(F2 v) { return v.hi; }
 inline F2 f2_add(F2 a, F2 b) { return F2{a.lo + b.lo, a.hi + b.hi}; }

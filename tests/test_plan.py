@@ -9,17 +9,27 @@ from tests import common
 def test_jacobi2d_time_block_4():
   p = plan.make_pass_plan(common.stencil('jacobi2d', iterate=64), time_block=4)
   assert [n.name for n in p.nodes][:2] == ['t1', 't1_iter1']
-  assert [n.lag for n in p.nodes] == [0, 1, 2, 3, 4]
+  # pipelined schedule (2-D default): a level reads what the level below had
+  # finished before the current step, so it trails it by 1 (row +1) + 1 step
+  assert p.skew == 1
+  assert [n.lag for n in p.nodes] == [0, 2, 4, 6, 8]
   # every level but the last is read at rows -1, 0, +1 by the next level
   assert [n.ring for n in p.nodes] == [3, 3, 3, 3, 1]
   assert p.nodes[-1].out == 0 and all(n.out < 0 for n in p.nodes[:-1])
   assert (p.cells, p.strip) == (4, 128)
   assert p.halo_lo == (4,) and p.halo_hi == (4,) and p.valid == (120,)
-  assert (p.lo_s, p.max_lag) == (-4, 4)
+  assert (p.lo_s, p.max_lag) == (-4, 8)
+  # producers-first schedule: the closed form of the reference's produce
+  # offsets (src/soda/core.py:371-446)
+  q = plan.make_pass_plan(common.stencil('jacobi2d', iterate=64), time_block=4,
+                          pipelined=False)
+  assert q.skew == 0 and [n.lag for n in q.nodes] == [0, 1, 2, 3, 4]
+  assert [n.ring for n in q.nodes] == [3, 3, 3, 3, 1]
+  assert (q.lo_s, q.max_lag) == (-4, 4)
 
 
 def test_one_sided_window_blur():
-  p = plan.make_pass_plan(common.stencil('blur'))
+  p = plan.make_pass_plan(common.stencil('blur'), pipelined=False)
   # uint16: 8 cells per lane (16-byte vectors, 16-byte aligned TMA boxes)
   assert (p.cells, p.strip, p.align0) == (8, 256, 8)
   assert p.halo_lo == (0,) and p.halo_hi == (2,)
@@ -32,7 +42,7 @@ def test_one_sided_window_blur():
 def test_off_centre_store_xcorr():
   """tmp1(0, 9) = sum input(0, 0..18): offsets are taken relative to the store
   index (src/soda/codegen/frt/host.py:587-592)."""
-  p = plan.make_pass_plan(common.stencil('xcorr'))
+  p = plan.make_pass_plan(common.stencil('xcorr'), pipelined=False)
   by_name = {n.name: n for n in p.nodes}
   assert by_name['tmp1'].lag == 9 and by_name['input'].ring == 19
   assert by_name['tmp2'].halo_lo == (9,) and by_name['tmp2'].halo_hi == (9,)
@@ -87,12 +97,13 @@ def test_generated_source_contains_no_kernels():
 
 
 def test_packed_fp32_eligibility():
-  """Packed FADD2/FMUL2 evaluation: fp32 star stencils only."""
+  """Packed FADD2/FFMA2 evaluation: fp32 programs that only add, subtract
+  and multiply."""
   want = {'jacobi2d': True, 'jacobi3d': True, 'heat3d': True,
-          'seidel2d': False,   # nine loads, six at odd dimension-0 offsets
+          'seidel2d': True,
           'blur': False, 'sobel2d': False, 'xcorr': False, 'erosion': False,
           'denoise2d': False, 'denoise3d': False,   # sqrt, division
-          'contrast': False}
+          'contrast': True}
   for name, flag in want.items():
     assert plan.packable(common.stencil(name)) == flag, name
   p = plan.make_pass_plan(common.stencil('jacobi2d'), time_block=2)

@@ -18,15 +18,27 @@ from soda_b200.codegen.cuda import build as cuda_build  # noqa: E402
 from soda_b200.codegen.cuda import launcher  # noqa: E402
 
 WIDTH = HEIGHT = 16384
-ITERATE = 16
+ITERATE = 120  # divisible by the time blocks compared below
 
 
 def variants():
-  for tb, warps, chunk, stages in itertools.product((1, 2, 4, 8), (4, 8),
-                                                    (6, 12), (3, 4)):
-    if tb == 8 and chunk == 12 and warps == 8:
-      pass
-    yield tb, {'warps': warps, 'chunk': chunk, 'stages': stages}
+  if os.environ.get('SODA_TUNE_SET') == 'wide':
+    # the launch-shape sweep of the first round
+    for tb, warps, chunk, stages in itertools.product((1, 2, 4, 8), (4, 8),
+                                                      (6, 12), (3, 4)):
+      yield tb, {'warps': warps, 'chunk': chunk, 'stages': stages}
+    return
+  for tb in (1, 2, 4, 5, 6, 8, 10):
+    yield tb, {}
+  for tb in (4, 5, 6, 8, 10):
+    yield tb, {'no_pipeline': True}
+    yield tb, {'no_pack': True}
+    yield tb, {'min_blocks': 3}
+    yield tb, {'min_blocks': 4}
+    yield tb, {'warps': 8}
+    yield tb, {'warps': 2, 'min_blocks': 6}
+  for tb in (4, 5, 6):
+    yield tb, {'cells': 8, 'stages': 3}
 
 
 def stencil():
