@@ -126,9 +126,11 @@ def tuning_2d(pass_plan: planner.PassPlan, options: Dict) -> Dict[str, int]:
   chunk = min(chunk, 256)
   return {
       'kWarps': options.get('warps') or 4,
+      'kCy': 1,
       'kMinBlocks': options.get('min_blocks') or 1,
       'kStages': options.get('stages') or 4,
       'kChunk': chunk,
+      'kUnroll': chunk,
   }
 
 
@@ -146,10 +148,31 @@ def tuning_3d(pass_plan: planner.PassPlan, options: Dict) -> Dict[str, int]:
                       abs(delta[1]) * pass_plan.strip + abs(delta[0]) +
                       pass_plan.cells)
   guard = (reach * elem + 127) // 128 * 128
+  stages = in_depth + (options.get('lookahead') or 2)
+  # unroll the step loop so that window rotation is register renaming and ring
+  # slots are compile-time constants, unless the DAG is large (code size)
+  rings = sorted({n.ring for n in pass_plan.nodes if n.ring > 1})
+  depths = sorted(
+      set(rings) | {stages} |
+      {n.smem_depth for n in pass_plan.nodes
+       if n.kind == 'stage' and n.smem_depth > 0})
+  unroll = options.get('unroll')
+  if not unroll:
+    work = sum(1 for n in pass_plan.nodes if n.kind == 'stage') * pass_plan.cy
+    unroll = 1
+    # ring depths first (rotation by renaming); shared-memory slot counts
+    # too if that stays small (compile-time slots), else they are computed
+    for candidate in (_lcm(depths), _lcm(rings) if rings else 1):
+      if candidate <= 6 and candidate * work <= 64:
+        unroll = candidate
+        break
   return {
       'kRows': pass_plan.rows,
+      'kCy': pass_plan.cy,
+      'kWarps': pass_plan.rows // pass_plan.cy,
+      'kUnroll': unroll,
       'kMinBlocks': options.get('min_blocks') or 1,
-      'kStages': in_depth + (options.get('lookahead') or 2),
+      'kStages': stages,
       'kInDepth': in_depth,
       'kGuardBytes': guard,
   }
@@ -198,13 +221,14 @@ def _emit_pass(ns: str, stencil, pass_plan: planner.PassPlan,
           'statement %s loads more than 8 distinct tensors' % node.name)
     prods = ', '.join(map(str, node.prods + [0] * (8 - len(node.prods))))
     lines.append(
-        '      {{{kind}, {src}, {lag}, {ring}, {out}, {smem}, {nprod}, {{{prods}}}}},'
+        '      {{{kind}, {src}, {lag}, {ring}, {out}, {smem}, {reach}, {nprod}, {{{prods}}}}},'
         '  // {id}: {name}'.format(kind=0 if node.kind == 'input' else 1,
                                   src=node.src,
                                   lag=node.lag,
                                   ring=node.ring,
                                   out=node.out,
                                   smem=node.smem_depth,
+                                  reach=node.smem_reach,
                                   nprod=len(node.prods),
                                   prods=prods,
                                   id=node.id,
@@ -247,6 +271,7 @@ def emit_program(stencil,
                                  # blocking, 32-row tiles with it (halo share)
                                  rows=options.get('rows') or (8 if tb == 1
                                                               else 32),
+                                 cy=options.get('cy') or 1,
                                  pack=False if options.get('no_pack') else None,
                                  pipelined=False
                                  if options.get('no_pipeline') else None)

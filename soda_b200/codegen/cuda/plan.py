@@ -54,8 +54,10 @@ class Node:
   # bounds of the dependency cone towards the pass inputs, per dimension
   win_lo: Tuple[int, ...] = ()
   win_hi: Tuple[int, ...] = ()
-  # 3-D only: planes kept in shared memory for dimension-1 neighbours
+  # 3-D only: planes kept in shared memory for dimension-1 neighbours, and
+  # the furthest dimension-1 offset at which any consumer reads them
   smem_depth: int = 0
+  smem_reach: int = 0
 
 
 @dataclasses.dataclass
@@ -81,7 +83,8 @@ class PassPlan:
   valid: Tuple[int, ...]  # valid cells per non-streamed dim per strip/tile
   lo_s: int  # lowest input slice (relative) an output slice depends on
   max_lag: int
-  rows: int = 1  # 3-D: tile rows (= warps per CTA)
+  rows: int = 1  # 3-D: tile rows (= warps per CTA * rows per thread)
+  cy: int = 1  # 3-D: rows of the patch one thread owns
   align0: int = 1  # strip origins are multiples of this many cells
   pack: int = 1  # cells evaluated per instruction (2: packed fp32 pairs)
   # 1: every node reads what its producers had produced *before* the current
@@ -192,11 +195,13 @@ def make_pass_plan(stencil,
                    time_block: int = 1,
                    cells: Optional[int] = None,
                    rows: int = 8,
+                   cy: int = 1,
                    pack: Optional[bool] = None,
                    pipelined: Optional[bool] = None) -> PassPlan:
   """Plans one pass of ``time_block`` fused iterations.
 
-  ``rows`` is only used by 3-D programs (tile height = warps per CTA).
+  ``rows`` and ``cy`` are only used by 3-D programs: a CTA covers ``rows``
+  tile rows with ``rows / cy`` warps, every thread owning ``cy`` rows.
 
   ``pipelined`` (2-D, default on): node ``n`` only reads slices its producers
   finished in an earlier step, so the nodes of one step do not depend on each
@@ -319,6 +324,7 @@ def make_pass_plan(stencil,
   for node in nodes:
     ring = 1
     smem_depth = 0
+    smem_reach = 0
     for consumer in nodes:
       for prod_id, deltas in zip(consumer.prods, consumer.deltas):
         if prod_id != node.id:
@@ -330,11 +336,15 @@ def make_pass_plan(stencil,
           if distance < step_skew:
             raise util.InternalError('consumer not behind its producer')
           if dim == 3 and delta[1] != 0:
+            # rows outside the consumer's patch come from shared memory ...
             smem_depth = max(smem_depth, distance + 1)
-          else:
+            smem_reach = max(smem_reach, abs(delta[1]))
+          if dim != 3 or delta[1] == 0 or cy > 1:
+            # ... all others from the register window
             ring = max(ring, distance + 1 - step_skew)
     node.ring = ring
     node.smem_depth = smem_depth
+    node.smem_reach = smem_reach
 
   outs = [n for n in nodes if n.out >= 0]
   halo_lo = [max(n.halo_lo[d] for n in outs) for d in range(dim - 1)]
@@ -354,6 +364,10 @@ def make_pass_plan(stencil,
         (halo_lo[0] + halo_hi[0], time_block, strip))
   valid = [valid0]
   if dim == 3:
+    if cy < 1 or rows % cy:
+      raise util.SemanticError(
+          'tile rows (%d) must be a multiple of the rows per thread (%d)' %
+          (rows, cy))
     valid1 = rows - halo_lo[1] - halo_hi[1]
     if valid1 <= 0:
       raise util.SemanticError(
@@ -375,6 +389,7 @@ def make_pass_plan(stencil,
                   lo_s=min(n.win_lo[s_dim] for n in outs),
                   max_lag=max(n.lag for n in outs),
                   rows=rows if dim == 3 else 1,
+                  cy=cy if dim == 3 else 1,
                   align0=align0,
                   pack=2 if (pack is not False and cells % 2 == 0 and
                              packable(stencil)) else 1,

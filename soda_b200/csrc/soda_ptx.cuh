@@ -131,13 +131,13 @@ __device__ __forceinline__ F2 f2_pack(float lo, float hi) {
   return r;
 }
 __device__ __forceinline__ float f2_lo(F2 v) {
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v.bits));
+  float lo;
+  asm("{ .reg .b32 hi; mov.b64 {%0, hi}, %1; }" : "=f"(lo) : "l"(v.bits));
   return lo;
 }
 __device__ __forceinline__ float f2_hi(F2 v) {
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v.bits));
+  float hi;
+  asm("{ .reg .b32 lo; mov.b64 {lo, %0}, %1; }" : "=f"(hi) : "l"(v.bits));
   return hi;
 }
 __device__ __forceinline__ F2 f2_add(F2 a, F2 b) {

@@ -294,7 +294,7 @@ int launch_pass_3d(const PassArgs& a) {
         kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes);
     if (attr_status == cudaSuccess)
       attr_status = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &ctas_per_sm, kernel, Prog::kRows * 32, S::kBytes);
+          &ctas_per_sm, kernel, Prog::kWarps * 32, S::kBytes);
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   });
   SODA_CUDA_CHECK(attr_status);
@@ -330,7 +330,7 @@ int launch_pass_3d(const PassArgs& a) {
                                 Prog::kMaxLag - Prog::kLoS, ctas_per_sm, a.segment);
   p.vec_ok = outputs_vector_aligned<Prog>(a) ? 1 : 0;
   dim3 grid(tiles_x, tiles_y, ceil_div(hi[2] - lo[2], p.seg_planes));
-  SODA_LAUNCH(kernel, grid, Prog::kRows * 32, S::kBytes, a.stream, p);
+  SODA_LAUNCH(kernel, grid, Prog::kWarps * 32, S::kBytes, a.stream, p);
   launch_counter().fetch_add(1);
   SODA_CUDA_CHECK(cudaGetLastError());
   return SODA_CUDA_OK;
@@ -361,7 +361,7 @@ soda_cuda_pass_info pass_info_of() {
     info.threads_per_cta = Prog::kWarps * 32;
     info.smem_bytes = Smem2D<Prog>::kBytes;
   } else {
-    info.threads_per_cta = Prog::kRows * 32;
+    info.threads_per_cta = Prog::kWarps * 32;
     info.smem_bytes = Smem3D<Prog>::kBytes;
     info.valid_cells[1] = Prog::kValid1;
   }

@@ -19,6 +19,7 @@
 //                                registers, before anything returns to HBM
 //   BurstRead / BurstWrite    -> TMA tiled loads into an mbarrier ring in
 //                                shared memory; 16-byte coalesced stores
+// A thread owns a patch of kCy rows x kCells cells (kCy == 1 in 2-D).
 //
 // Step t of a strip consumes input slice t; node n then produces its slice
 // t - lag[n].  Values computed from cells outside the loaded tile are garbage
@@ -46,6 +47,7 @@ struct NodeDesc {
   int ring;        // slices kept in the register window (>= 1)
   int out;         // output array stored by this node, or -1
   int smem_depth;  // 3-D: slices readable by other warps (0: none)
+  int smem_reach;  // 3-D: furthest dimension-1 offset at which it is read
   int nprod;
   int prod[kMaxProds];  // producer node per functor load slot
 };
@@ -142,7 +144,7 @@ __device__ __forceinline__ void cells_from_units(
 // ---- register sliding windows ------------------------------------------------
 template <class Prog, int N>
 struct RingStore : RingStore<Prog, N - 1> {
-  UnitOf<Prog, N - 1> r[Prog::kNodes[N - 1].ring][kUnitsOf<Prog>];
+  UnitOf<Prog, N - 1> r[Prog::kNodes[N - 1].ring][Prog::kCy][kUnitsOf<Prog>];
 };
 template <class Prog>
 struct RingStore<Prog, 0> {};
@@ -167,11 +169,14 @@ __device__ __forceinline__ void clear_rings(Rings<Prog>& rings) {
 #pragma unroll
     for (int s = 0; s < Prog::kNodes[N].ring; ++s) {
 #pragma unroll
-      for (int u = 0; u < kUnitsOf<Prog>; ++u) {
-        if constexpr (Prog::kPack == 2) {
-          r[s][u] = f2_splat(0.0f);
-        } else {
-          r[s][u] = T(0);
+      for (int j = 0; j < Prog::kCy; ++j) {
+#pragma unroll
+        for (int u = 0; u < kUnitsOf<Prog>; ++u) {
+          if constexpr (Prog::kPack == 2) {
+            r[s][j][u] = f2_splat(0.0f);
+          } else {
+            r[s][j][u] = T(0);
+          }
         }
       }
     }
@@ -179,41 +184,68 @@ __device__ __forceinline__ void clear_rings(Rings<Prog>& rings) {
   }
 }
 
+// Register slot that holds logical slot `logical` (0: oldest, ring-1: the slice
+// of this step) of node P.  Contexts that know their phase within an unrolled
+// loop (Ctx::kRotate) use the window as a circular buffer with compile-time
+// indices whenever the unroll factor is a multiple of the depth: nothing is
+// ever copied.  Otherwise the window is shifted every step.
+template <class Prog, class Ctx, int P>
+__host__ __device__ constexpr bool ring_rotates() {
+  return Ctx::kRotate && Prog::kUnroll % Prog::kNodes[P].ring == 0;
+}
+template <class Prog, class Ctx, int P>
+__host__ __device__ constexpr int phys_slot(int logical) {
+  constexpr int kDepth = Prog::kNodes[P].ring;
+  if (ring_rotates<Prog, Ctx, P>()) {
+    return ((Ctx::kPhase - (kDepth - 1 - logical)) % kDepth + kDepth) % kDepth;
+  }
+  return logical;
+}
+
 // Oldest slice falls out, slot ring-1 becomes free for the slice of this step.
-// With the step loop unrolled by a multiple of the ring depth the copies are
-// pure register renaming.
-template <int N, class Prog>
-__device__ __forceinline__ void advance_ring(Rings<Prog>& rings) {
-  auto& r = ring_of<N, Prog>(rings);
+template <int N, class Prog, class Ctx>
+__device__ __forceinline__ void advance_ring(Ctx& ctx) {
+  if constexpr (!ring_rotates<Prog, Ctx, N>()) {
+    auto& r = ring_of<N, Prog>(ctx.rings);
 #pragma unroll
-  for (int s = 0; s + 1 < Prog::kNodes[N].ring; ++s) {
+    for (int s = 0; s + 1 < Prog::kNodes[N].ring; ++s) {
 #pragma unroll
-    for (int u = 0; u < kUnitsOf<Prog>; ++u) r[s][u] = r[s + 1][u];
+      for (int j = 0; j < Prog::kCy; ++j) {
+#pragma unroll
+        for (int u = 0; u < kUnitsOf<Prog>; ++u) r[s][j][u] = r[s + 1][j][u];
+      }
+    }
   }
 }
 
-// The newest slice of node N as plain cells (for stores and exports).
-template <int N, class Prog>
+// The units of patch row J of the slice node N produces in this step.
+template <int N, int J, class Prog, class Ctx>
+__device__ __forceinline__ auto& newest_units(Ctx& ctx) {
+  return ring_of<N, Prog>(ctx.rings)[phys_slot<Prog, Ctx, N>(
+      Prog::kNodes[N].ring - 1)][J];
+}
+
+// ... as plain cells (for stores).
+template <int N, int J, class Prog, class Ctx>
 __device__ __forceinline__ void newest_cells(
-    const Rings<Prog>& rings,
-    typename Prog::template T<N> (&cells)[Prog::kCells]) {
-  cells_from_units<Prog, N>(
-      cells, ring_of<N, Prog>(rings)[Prog::kNodes[N].ring - 1]);
+    Ctx& ctx, typename Prog::template T<N> (&cells)[Prog::kCells]) {
+  cells_from_units<Prog, N>(cells, newest_units<N, J, Prog>(ctx));
 }
 
 // ---- accessor handed to the generated functors --------------------------------
 // ld<K, DX, DY, DS>() is the value of the K-th loaded tensor of the statement
 // at offset (DX, DY, DS) from the unit being produced (DY is always 0 in 2-D;
-// DS is the offset in the streamed dimension).  I is the unit index within the
-// lane.  Cells the lane does not own come from the neighbouring lanes by warp
-// shuffle; dimension-1 neighbours (3-D) from shared memory.
-template <class Prog, class Ctx, int N, int I>
+// DS is the offset in the streamed dimension).  J is the row of the thread's
+// patch, I the unit index within that row.  Cells the lane does not own come
+// from the neighbouring lanes by warp shuffle; rows outside the patch (3-D)
+// from shared-memory planes.
+template <class Prog, class Ctx, int N, int J, int I>
 struct Access {
   const Ctx& ctx;
 
-  // one cell of producer P's slice in register slot kSlot, by cell index
-  // relative to the lane's first cell
-  template <int P, int kSlot, int kCell>
+  // one cell of producer P's slice in register slot kSlot, patch row kRow, by
+  // cell index relative to the lane's first cell
+  template <int P, int kSlot, int kRow, int kCell>
   __device__ __forceinline__ typename Prog::template T<P> cell() const {
     constexpr int kC = Prog::kCells;
     constexpr int kLane = floor_div(kCell, kC);
@@ -221,10 +253,10 @@ struct Access {
     typename Prog::template T<P> v;
     if constexpr (Prog::kPack == 2) {
       constexpr int kH = kUnitsOf<Prog>;
-      const F2 unit = ring_of<P, Prog>(ctx.rings)[kSlot][kLocal % kH];
+      const F2 unit = ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal % kH];
       v = kLocal >= kH ? f2_hi(unit) : f2_lo(unit);
     } else {
-      v = ring_of<P, Prog>(ctx.rings)[kSlot][kLocal];
+      v = ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal];
     }
     if constexpr (kLane == 0) {
       return v;
@@ -244,19 +276,22 @@ struct Access {
     // second one is kHalf cells further)
     constexpr int kFirst = I + DX;
     constexpr int kHalf = kUnitsOf<Prog>;
-    if constexpr (DY == 0) {
+    constexpr int kRow = J + DY;
+    if constexpr (kRow >= 0 && kRow < Prog::kCy) {
       // pipelined plans (kSkew == 1) evaluate a node before its producers
       // advance in the same step: their newest slice is one step old
-      constexpr int kSlot = Prog::kNodes[P].ring - 1 - (kDistance - Prog::kSkew);
-      static_assert(kSlot >= 0, "plan: register window too short");
+      constexpr int kLogical =
+          Prog::kNodes[P].ring - 1 - (kDistance - Prog::kSkew);
+      static_assert(kLogical >= 0, "plan: register window too short");
+      constexpr int kSlot = phys_slot<Prog, Ctx, P>(kLogical);
       if constexpr (Prog::kPack == 1) {
-        return cell<P, kSlot, kFirst>();
+        return cell<P, kSlot, kRow, kFirst>();
       } else {
         constexpr int kLane = floor_div(kFirst, Prog::kCells);
         constexpr int kLocal = kFirst - kLane * Prog::kCells;
         if constexpr (kLocal < kHalf) {
           // a whole unit of this or a neighbouring lane
-          const F2 v = ring_of<P, Prog>(ctx.rings)[kSlot][kLocal];
+          const F2 v = ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal];
           if constexpr (kLane == 0) {
             return v;
           } else {
@@ -265,7 +300,7 @@ struct Access {
         } else {
           // rotated across a lane boundary: (hi of unit j in lane kLane,
           // lo of unit j in lane kLane + 1)
-          const F2 v = ring_of<P, Prog>(ctx.rings)[kSlot][kLocal - kHalf];
+          const F2 v = ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal - kHalf];
           float first = f2_hi(v);
           float second = f2_lo(v);
           if constexpr (kLane != 0) first = shfl_rel<kLane>(first);
@@ -278,24 +313,25 @@ struct Access {
       static_assert(kDistance < Prog::kNodes[P].smem_depth,
                     "plan: shared-memory window too short");
       if constexpr (Prog::kPack == 1) {
-        return ctx.template plane_load<P, kDistance, kFirst, DY>();
+        return ctx.template plane_cell<P, kDistance, kFirst, kRow>();
       } else {
-        return f2_pack(
-            ctx.template plane_load<P, kDistance, kFirst, DY>(),
-            ctx.template plane_load<P, kDistance, kFirst + kHalf, DY>());
+        return ctx.template plane_unit<P, kDistance, kFirst, kRow>();
       }
     }
   }
 };
 
-template <class Prog, class Ctx, int N, int I = 0>
+// every unit of every patch row of node N
+template <class Prog, class Ctx, int N, int K = 0>
 __device__ __forceinline__ void eval_units(Ctx& ctx) {
-  if constexpr (I < kUnitsOf<Prog>) {
+  if constexpr (K < Prog::kCy * kUnitsOf<Prog>) {
     using T = typename Prog::template T<N>;
     using F = typename Prog::template StageF<Prog::kNodes[N].src>;
-    ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1][I] =
-        cast_to<T>(F::eval(Access<Prog, Ctx, N, I>{ctx}));
-    eval_units<Prog, Ctx, N, I + 1>(ctx);
+    constexpr int J = K / kUnitsOf<Prog>;
+    constexpr int I = K % kUnitsOf<Prog>;
+    newest_units<N, J, Prog>(ctx)[I] =
+        cast_to<T>(F::eval(Access<Prog, Ctx, N, J, I>{ctx}));
+    eval_units<Prog, Ctx, N, K + 1>(ctx);
   }
 }
 
@@ -410,6 +446,8 @@ struct Smem2D {
 
 template <class Prog>
 struct Ctx2D {
+  static constexpr bool kRotate = false;  // windows are shifted every step
+  static constexpr int kPhase = 0;
   Rings<Prog> rings;
   const Params2D<Prog>& p;
   const unsigned char* slot_base;  // current slot of the TMA ring
@@ -447,7 +485,7 @@ __device__ __forceinline__ void store_node_2d(Ctx& ctx, int t) {
   using T = typename Prog::template T<N>;
   constexpr int kOut = Prog::kNodes[N].out;
   T cells[Prog::kCells];
-  newest_cells<N, Prog>(ctx.rings, cells);
+  newest_cells<N, 0, Prog>(ctx, cells);
   store_slice<T, Prog::kCells>(ctx.store[kOut], cells,
                                t - Prog::kNodes[N].lag, ctx.any_partial);
 }
@@ -457,7 +495,7 @@ __device__ __forceinline__ void store_node_2d(Ctx& ctx, int t) {
 template <class Prog, class Ctx, int N>
 __device__ __forceinline__ void step_node_2d(Ctx& ctx, int t, int r) {
   using T = typename Prog::template T<N>;
-  advance_ring<N, Prog>(ctx.rings);
+  advance_ring<N, Prog>(ctx);
   if constexpr (Prog::kNodes[N].kind == 0) {
     constexpr int M = Prog::kNodes[N].src;
     using S = Smem2D<Prog>;
@@ -466,8 +504,7 @@ __device__ __forceinline__ void step_node_2d(Ctx& ctx, int t, int r) {
         r * S::template row_bytes<M>());
     T cells[Prog::kCells];
     load_shared_vec<T, Prog::kCells>(cells, row + ctx.lane * Prog::kCells);
-    units_from_cells<Prog, N>(
-        ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1], cells);
+    units_from_cells<Prog, N>(newest_units<N, 0, Prog>(ctx), cells);
   } else {
     eval_units<Prog, Ctx, N>(ctx);
   }
@@ -568,10 +605,17 @@ __global__ void __launch_bounds__(Prog::kWarps * 32, Prog::kMinBlocks)
 }
 
 // =============================================================================
-// 3-D: a CTA streams a (strip x rows) tile along the last dimension; warp w owns
-// tile row w.  Dimension-0 neighbours: warp shuffles.  Dimension-1 neighbours:
-// shared-memory planes (the TMA ring for inputs, an export ring for stages),
-// read one step after they were written so that one barrier per step suffices.
+// 3-D: a CTA streams a (strip x rows) tile along the last dimension.  Warp w
+// owns the kCy tile rows [w * kCy, (w + 1) * kCy); a thread therefore holds a
+// patch of kCy rows x kCells cells of every node in its register windows.
+//   dimension-0 neighbours: warp shuffles (as in 2-D)
+//   dimension-1 neighbours: registers inside the patch, shared-memory planes
+//     outside it - the TMA ring itself for pass inputs, an export ring for
+//     fused stages, read one step after they were written so that one CTA
+//     barrier per step orders exports, their readers and the TMA slot reuse
+//   streamed dimension: register windows
+// The step loop is unrolled kUnroll times; ring depths that divide kUnroll get
+// compile-time slots and window rotation by register renaming.
 // =============================================================================
 
 template <class Prog>
@@ -629,22 +673,56 @@ struct Smem3D {
   static constexpr int kBytes = kBarrierOffset + int(sizeof(Mbarrier)) * kStages;
 };
 
+// Where the cells of a lane's vector sit in a shared-memory plane.  TMA writes
+// input planes in grid order; exported planes of packed programs keep the
+// register order (lo, hi of unit 0, lo, hi of unit 1, ...) so that exports and
+// aligned reloads are plain vector moves.
+template <class Prog, int P>
+__host__ __device__ constexpr int plane_index(int local) {
+  if (Prog::kPack == 2 && Prog::kNodes[P].kind == 1) {
+    return (local % kUnitsOf<Prog>) * 2 + local / kUnitsOf<Prog>;
+  }
+  return local;
+}
+
 template <class Prog>
 struct Ctx3D {
-  Rings<Prog> rings;
   const Params3D<Prog>& p;
   unsigned char* smem;
   int lane;
-  int row;       // tile row owned by this warp
+  int row;       // first tile row of the thread's patch (warp * kCy)
   int cell_off;  // row * kStrip + lane * kCells
-  int step;      // steps since the start of the segment
+  int step;      // steps since the start of the segment (start of the round)
   int x0, y0;
   int seg_lo, seg_hi;
+  // stores: one plan per output for patch row 0; the other rows are
+  // out_pitch apart and only differ in whether they are stored at all
   StorePlan store[Prog::kNumOutputs];
+  unsigned row_mask[Prog::kNumOutputs];
   bool any_partial;
 
   __device__ __forceinline__ explicit Ctx3D(const Params3D<Prog>& params)
       : p(params) {}
+};
+
+// What the functors see during step (round start + U) of the unrolled loop.
+template <class Prog, int U>
+struct Step3D {
+  static constexpr bool kRotate = true;
+  static constexpr int kPhase = U;
+  Rings<Prog>& rings;
+  Ctx3D<Prog>& c;
+
+  // slot of a ring of kDepth slots that held step (current - kDistance)
+  template <int kDepth, int kDistance>
+  __device__ __forceinline__ int slot() const {
+    if constexpr (Prog::kUnroll % kDepth == 0) {
+      return ((U - kDistance) % kDepth + kDepth) % kDepth;
+    } else {
+      return (c.step + U + kDepth * (kDistance / kDepth + 1) - kDistance) %
+             kDepth;
+    }
+  }
 
   // Plane of node P produced kDistance steps before P's current one.
   template <int P, int kDistance>
@@ -652,23 +730,42 @@ struct Ctx3D {
     using S = Smem3D<Prog>;
     using T = typename Prog::template T<P>;
     if constexpr (Prog::kNodes[P].kind == 0) {
-      constexpr int kStages = S::kStages;
-      const int slot = (step + kStages - kDistance) % kStages;
       return reinterpret_cast<const T*>(
-          smem + S::kRingOffset + slot * S::kSlotBytes +
+          c.smem + S::kRingOffset +
+          slot<S::kStages, kDistance>() * S::kSlotBytes +
           S::template input_offset<Prog::kNodes[P].src>());
     } else {
       constexpr int kDepth = Prog::kNodes[P].smem_depth;
-      const int slot = (step + kDepth - kDistance) % kDepth;
       return reinterpret_cast<const T*>(
-          smem + S::kExportOffset + S::template export_offset<P>() +
-          slot * S::template plane_bytes<P>());
+          c.smem + S::kExportOffset + S::template export_offset<P>() +
+          slot<kDepth, kDistance>() * S::template plane_bytes<P>());
     }
   }
 
-  template <int P, int kDistance, int kCol, int kDy>
-  __device__ __forceinline__ typename Prog::template T<P> plane_load() const {
-    return plane<P, kDistance>()[cell_off + kDy * Prog::kStrip + kCol];
+  // the vector of the lane kLaneOff lanes away, patch row kRow (any sign)
+  template <int P, int kDistance, int kRow, int kLaneOff>
+  __device__ __forceinline__ Vec<typename Prog::template T<P>, Prog::kCells>
+  plane_vec() const {
+    using T = typename Prog::template T<P>;
+    return *reinterpret_cast<const Vec<T, Prog::kCells>*>(
+        plane<P, kDistance>() + c.cell_off + kRow * Prog::kStrip +
+        kLaneOff * Prog::kCells);
+  }
+
+  template <int P, int kDistance, int kCol, int kRow>
+  __device__ __forceinline__ typename Prog::template T<P> plane_cell() const {
+    constexpr int kLane = floor_div(kCol, Prog::kCells);
+    constexpr int kLocal = kCol - kLane * Prog::kCells;
+    return plane_vec<P, kDistance, kRow, kLane>()
+        .v[plane_index<Prog, P>(kLocal)];
+  }
+
+  // packed: cells (kCol, kCol + kCells / 2)
+  template <int P, int kDistance, int kCol, int kRow>
+  __device__ __forceinline__ F2 plane_unit() const {
+    constexpr int kHalf = kUnitsOf<Prog>;
+    return f2_pack(plane_cell<P, kDistance, kCol, kRow>(),
+                   plane_cell<P, kDistance, kCol + kHalf, kRow>());
   }
 };
 
@@ -679,58 +776,124 @@ __device__ __forceinline__ void init_stores_3d(Ctx3D<Prog>& ctx, int t_begin) {
     using T = typename Prog::template T<N>;
     constexpr int kC = Prog::kCells;
     const int col_in_strip = ctx.lane * kC;
-    const int y = ctx.y0 + ctx.row;
-    const bool lane_ok =
-        col_in_strip >= Prog::kHaloLo0 &&
-        col_in_strip + kC <= Prog::kHaloLo0 + Prog::kValid0 &&
-        ctx.row >= Prog::kHaloLo1 && ctx.row < Prog::kHaloLo1 + Prog::kValid1 &&
-        y >= ctx.p.box_lo[O][1] && y < ctx.p.box_hi[O][1];
+    const int y = ctx.y0 + ctx.row;  // patch row 0
+    unsigned rows = 0;
+#pragma unroll
+    for (int j = 0; j < Prog::kCy; ++j) {
+      const int tile_row = ctx.row + j;
+      if (tile_row >= Prog::kHaloLo1 &&
+          tile_row < Prog::kHaloLo1 + Prog::kValid1 &&
+          y + j >= ctx.p.box_lo[O][1] && y + j < ctx.p.box_hi[O][1])
+        rows |= 1u << j;
+    }
+    const bool lane_ok = col_in_strip >= Prog::kHaloLo0 &&
+                         col_in_strip + kC <= Prog::kHaloLo0 + Prog::kValid0 &&
+                         rows != 0;
     init_store_plan<T, kC>(
         ctx.store[O], ctx.p.out[O],
         static_cast<long long>(y) * ctx.p.out_pitch[O], ctx.p.out_plane_pitch[O],
         ctx.x0 + col_in_strip, lane_ok, ctx.p.box_lo[O][0], ctx.p.box_hi[O][0],
         ctx.p.vec_ok != 0, max(ctx.seg_lo, ctx.p.box_lo[O][2]),
         min(ctx.seg_hi, ctx.p.box_hi[O][2]), t_begin - Prog::kNodes[N].lag);
+    ctx.row_mask[O] = ctx.store[O].mode == 0 ? 0u : rows;
     init_stores_3d<Prog, O + 1>(ctx, t_begin);
   }
 }
 
-template <class Prog, class Ctx, int N>
-__device__ __forceinline__ void store_node_3d(Ctx& ctx, int t) {
-  using T = typename Prog::template T<N>;
-  constexpr int kOut = Prog::kNodes[N].out;
-  T cells[Prog::kCells];
-  newest_cells<N, Prog>(ctx.rings, cells);
-  store_slice<T, Prog::kCells>(ctx.store[kOut], cells,
-                               t - Prog::kNodes[N].lag, ctx.any_partial);
-}
-
-template <class Prog, class Ctx, int N = 0>
-__device__ __forceinline__ void step_nodes_3d(Ctx& ctx, int t) {
-  if constexpr (N < Prog::kNumNodes) {
+template <class Prog, class Step, int N, int J = 0>
+__device__ __forceinline__ void store_rows_3d(Step& st, unsigned char* ptr) {
+  if constexpr (J < Prog::kCy) {
     using T = typename Prog::template T<N>;
+    constexpr int kOut = Prog::kNodes[N].out;
     constexpr int kC = Prog::kCells;
-    advance_ring<N, Prog>(ctx.rings);
-    if constexpr (Prog::kNodes[N].kind == 0) {
+    const Ctx3D<Prog>& ctx = st.c;
+    const StorePlan& plan = ctx.store[kOut];
+    if ((ctx.row_mask[kOut] >> J) & 1u) {
       T cells[kC];
-      load_shared_vec<T, kC>(cells, ctx.template plane<N, 0>() + ctx.cell_off);
-      units_from_cells<Prog, N>(
-          ring_of<N, Prog>(ctx.rings)[Prog::kNodes[N].ring - 1], cells);
-    } else {
-      eval_units<Prog, Ctx, N>(ctx);
-      if constexpr (Prog::kNodes[N].smem_depth > 0) {
-        // export for the dimension-1 neighbours (read from the next step on)
-        T* dst = const_cast<T*>(ctx.template plane<N, 0>()) + ctx.cell_off;
-        T cells[kC];
-        newest_cells<N, Prog>(ctx.rings, cells);
-        Vec<T, kC> tmp;
+      newest_cells<N, J, Prog>(st, cells);
+      T* dst = reinterpret_cast<T*>(ptr) + J * ctx.p.out_pitch[kOut];
+      if (!ctx.any_partial) {
+        store_global_vec<T, kC>(dst, cells);
+      } else {
 #pragma unroll
-        for (int i = 0; i < kC; ++i) tmp.v[i] = cells[i];
-        *reinterpret_cast<Vec<T, kC>*>(dst) = tmp;
+        for (int i = 0; i < kC; ++i) {
+          if ((plan.mask >> i) & 1u) dst[i] = cells[i];
+        }
       }
     }
-    if constexpr (Prog::kNodes[N].out >= 0) store_node_3d<Prog, Ctx, N>(ctx, t);
-    step_nodes_3d<Prog, Ctx, N + 1>(ctx, t);
+    store_rows_3d<Prog, Step, N, J + 1>(st, ptr);
+  }
+}
+
+template <class Prog, class Step, int N>
+__device__ __forceinline__ void store_node_3d(Step& st, int t) {
+  constexpr int kOut = Prog::kNodes[N].out;
+  StorePlan& plan = st.c.store[kOut];
+  unsigned char* ptr = plan.ptr;
+  plan.ptr += plan.step;
+  const int slice = t - Prog::kNodes[N].lag;
+  if (slice < plan.slice_lo || slice >= plan.slice_hi) return;  // uniform
+  // without partial lanes in the warp, mode is 0 (row_mask == 0) or 1
+  store_rows_3d<Prog, Step, N>(st, ptr);
+}
+
+// rows of the patch that other warps read: the kReach rows next to each edge
+template <class Prog, class Step, int N, int J = 0>
+__device__ __forceinline__ void export_rows_3d(Step& st) {
+  if constexpr (J < Prog::kCy) {
+    constexpr int kReach = Prog::kNodes[N].smem_reach;
+    if constexpr (J < kReach || J >= Prog::kCy - kReach) {
+      using T = typename Prog::template T<N>;
+      constexpr int kC = Prog::kCells;
+      T* dst = const_cast<T*>(st.template plane<N, 0>()) + st.c.cell_off +
+               J * Prog::kStrip;
+      Vec<T, kC> tmp;
+      if constexpr (Prog::kPack == 2) {
+        const auto& units = newest_units<N, J, Prog>(st);
+#pragma unroll
+        for (int u = 0; u < kUnitsOf<Prog>; ++u) {
+          tmp.v[2 * u] = f2_lo(units[u]);
+          tmp.v[2 * u + 1] = f2_hi(units[u]);
+        }
+      } else {
+        T cells[kC];
+        newest_cells<N, J, Prog>(st, cells);
+#pragma unroll
+        for (int i = 0; i < kC; ++i) tmp.v[i] = cells[i];
+      }
+      *reinterpret_cast<Vec<T, kC>*>(dst) = tmp;
+    }
+    export_rows_3d<Prog, Step, N, J + 1>(st);
+  }
+}
+
+template <class Prog, class Step, int N, int J = 0>
+__device__ __forceinline__ void load_input_rows_3d(Step& st) {
+  if constexpr (J < Prog::kCy) {
+    using T = typename Prog::template T<N>;
+    T cells[Prog::kCells];
+    load_shared_vec<T, Prog::kCells>(
+        cells, st.template plane<N, 0>() + st.c.cell_off + J * Prog::kStrip);
+    units_from_cells<Prog, N>(newest_units<N, J, Prog>(st), cells);
+    load_input_rows_3d<Prog, Step, N, J + 1>(st);
+  }
+}
+
+template <class Prog, class Step, int N = 0>
+__device__ __forceinline__ void step_nodes_3d(Step& st, int t) {
+  if constexpr (N < Prog::kNumNodes) {
+    advance_ring<N, Prog>(st);
+    if constexpr (Prog::kNodes[N].kind == 0) {
+      load_input_rows_3d<Prog, Step, N>(st);
+    } else {
+      eval_units<Prog, Step, N>(st);
+      // export for the dimension-1 neighbours (read from the next step on)
+      if constexpr (Prog::kNodes[N].smem_depth > 0)
+        export_rows_3d<Prog, Step, N>(st);
+    }
+    if constexpr (Prog::kNodes[N].out >= 0)
+      store_node_3d<Prog, Step, N>(st, t);
+    step_nodes_3d<Prog, Step, N + 1>(st, t);
   }
 }
 
@@ -746,29 +909,63 @@ __device__ __forceinline__ void issue_plane_3d(const Params3D<Prog>& p,
   }
 }
 
+// steps [round, round + kUnroll) of the segment.  There is no per-step guard:
+// the kernel rounds the number of steps up to a multiple of kUnroll (planes
+// past the end of the grid are zero-filled by TMA and nothing is stored for
+// them), so that the register windows rotate by renaming across the round.
+template <class Prog, int U = 0>
+__device__ __forceinline__ void round_3d(Rings<Prog>& rings, Ctx3D<Prog>& ctx,
+                                         Mbarrier* full, int t_begin,
+                                         int num_steps) {
+  if constexpr (U < Prog::kUnroll) {
+    using S = Smem3D<Prog>;
+    constexpr int kStages = S::kStages;
+    constexpr int kInDepth = Prog::kInDepth;  // input planes still readable
+    const int step = ctx.step + U;
+    Step3D<Prog, U> st{rings, ctx};
+    const int slot = st.template slot<kStages, 0>();
+    mbar_wait(&full[slot], (static_cast<unsigned>(step) / kStages) & 1u);
+    step_nodes_3d<Prog>(st, t_begin + step);
+    cta_sync();  // exports visible; plane (step - kInDepth + 1) is dead
+    if (threadIdx.x < 32) {  // warp-uniform
+      const int dead = step - (kInDepth - 1);
+      if (ctx.lane == 0 && dead >= 0 && dead + kStages < num_steps) {
+        const int s = st.template slot<kStages, kInDepth - 1>();
+        mbar_arrive_expect_tx(&full[s], S::kSlotBytes);
+        issue_plane_3d<Prog>(ctx.p, ctx.smem + S::kRingOffset + s * S::kSlotBytes,
+                             ctx.x0, ctx.y0, t_begin + dead + kStages, &full[s]);
+      }
+    }
+    round_3d<Prog, U + 1>(rings, ctx, full, t_begin, num_steps);
+  }
+}
+
 template <class Prog>
-__global__ void __launch_bounds__(Prog::kRows * 32, Prog::kMinBlocks)
+__global__ void __launch_bounds__(Prog::kWarps * 32, Prog::kMinBlocks)
     soda_stream3d_kernel(const __grid_constant__ Params3D<Prog> p) {
   using S = Smem3D<Prog>;
   constexpr int kStages = S::kStages;
-  constexpr int kInDepth = Prog::kInDepth;  // input planes still readable
-  static_assert(kStages > kInDepth, "TMA ring needs look-ahead slots");
+  static_assert(kStages > Prog::kInDepth, "TMA ring needs look-ahead slots");
+  static_assert(Prog::kRows == Prog::kWarps * Prog::kCy, "tile rows");
 
+  Rings<Prog> rings;
   Ctx3D<Prog> ctx(p);
   ctx.smem = dyn_smem();
   ctx.lane = lane_id();
-  ctx.row = threadIdx.x >> 5;
+  ctx.row = (threadIdx.x >> 5) * Prog::kCy;
   ctx.cell_off = ctx.row * Prog::kStrip + ctx.lane * Prog::kCells;
   ctx.x0 = p.x_origin + blockIdx.x * Prog::kValid0 - Prog::kHaloLo0;
   ctx.y0 = p.y_origin + blockIdx.y * Prog::kValid1 - Prog::kHaloLo1;
   ctx.seg_lo = p.plane_lo + blockIdx.z * p.seg_planes;
   ctx.seg_hi = min(ctx.seg_lo + p.seg_planes, p.plane_hi);
-  clear_rings<Prog>(ctx.rings);
+  clear_rings<Prog>(rings);
 
   Mbarrier* full = reinterpret_cast<Mbarrier*>(ctx.smem + S::kBarrierOffset);
   unsigned char* ring = ctx.smem + S::kRingOffset;
   const int t_begin = ctx.seg_lo + Prog::kLoS;
-  const int num_steps = ctx.seg_hi - 1 + Prog::kMaxLag - t_begin + 1;
+  const int num_steps =
+      (ctx.seg_hi - 1 + Prog::kMaxLag - t_begin + Prog::kUnroll) /
+      Prog::kUnroll * Prog::kUnroll;
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -791,24 +988,8 @@ __global__ void __launch_bounds__(Prog::kRows * 32, Prog::kMinBlocks)
   }
   cta_sync();
 
-  int slot = 0;
-  unsigned parity = 0;
-  for (ctx.step = 0; ctx.step < num_steps; ++ctx.step) {
-    mbar_wait(&full[slot], parity);
-    step_nodes_3d<Prog>(ctx, t_begin + ctx.step);
-    cta_sync();  // exports visible; plane (step - kInDepth + 1) is dead
-    const int dead = ctx.step - (kInDepth - 1);
-    if (threadIdx.x == 0 && dead >= 0 && dead + kStages < num_steps) {
-      const int s = dead % kStages;
-      mbar_arrive_expect_tx(&full[s], S::kSlotBytes);
-      issue_plane_3d<Prog>(p, ring + s * S::kSlotBytes, ctx.x0, ctx.y0,
-                           t_begin + dead + kStages, &full[s]);
-    }
-    if (++slot == kStages) {
-      slot = 0;
-      parity ^= 1u;
-    }
-  }
+  for (ctx.step = 0; ctx.step < num_steps; ctx.step += Prog::kUnroll)
+    round_3d<Prog>(rings, ctx, full, t_begin, num_steps);
 }
 
 }  // namespace soda

@@ -47,6 +47,16 @@ CASES_3D = [
     ('heat3d', dict(extent=(40, 30, 9), time_block=1, iterate=2,
                     options={'rows': 4}, segment=5)),
     ('denoise3d', dict(extent=(140, 19, 7), options={'rows': 8}, segment=4)),
+    # patches: every thread owns cy rows of the tile
+    ('jacobi3d', dict(extent=(150, 25, 11), time_block=2, iterate=3,
+                      options={'rows': 16, 'cy': 4}, segment=6)),
+    ('heat3d', dict(extent=(40, 30, 9), time_block=1, iterate=2,
+                    options={'rows': 8, 'cy': 2}, segment=5)),
+    ('heat3d', dict(extent=(40, 30, 9), time_block=3, iterate=3,
+                    options={'rows': 16, 'cy': 2, 'no_pack': True})),
+    ('denoise3d', dict(extent=(140, 19, 7), options={'rows': 8, 'cy': 2},
+                       segment=4)),
+    ('denoise3d', dict(extent=(40, 33, 6), options={'rows': 16, 'cy': 4})),
 ]
 
 

@@ -28,17 +28,18 @@ def variants():
                                                       (6, 12), (3, 4)):
       yield tb, {'warps': warps, 'chunk': chunk, 'stages': stages}
     return
-  for tb in (1, 2, 4, 5, 6, 8, 10):
-    yield tb, {}
-  for tb in (4, 5, 6, 8, 10):
+  for tb in (5, 6, 8):
     yield tb, {'no_pipeline': True}
-    yield tb, {'no_pack': True}
-    yield tb, {'min_blocks': 3}
-    yield tb, {'min_blocks': 4}
-    yield tb, {'warps': 8}
-    yield tb, {'warps': 2, 'min_blocks': 6}
-  for tb in (4, 5, 6):
-    yield tb, {'cells': 8, 'stages': 3}
+  for tb in (4, 5, 6, 7, 8, 10):
+    for stages in (2, 3):
+      for warps in (2, 4):
+        yield tb, {'cells': 8, 'stages': stages, 'warps': warps,
+                   'no_pipeline': True}
+    yield tb, {'cells': 8, 'stages': 3, 'warps': 4}
+    yield tb, {'cells': 8, 'stages': 3, 'warps': 4, 'no_pipeline': True,
+               'no_pack': True}
+    yield tb, {'cells': 8, 'stages': 3, 'warps': 4, 'no_pipeline': True,
+               'chunk': 3}
 
 
 def stencil():
