@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 WIDTH = 16384
 HEIGHT = 16384
 ITERATE = 64
-TIME_BLOCK = int(os.environ.get('SODA_BENCH_TIME_BLOCK', '5'))
+TIME_BLOCK = int(os.environ.get('SODA_BENCH_TIME_BLOCK', '6'))
 PROGRAM = 'jacobi2d'
 BYTES_PER_CELL_PER_PASS = 8  # one fp32 read + one fp32 write
 FALLBACK_HBM_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md

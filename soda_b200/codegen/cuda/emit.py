@@ -128,10 +128,24 @@ def tuning_2d(pass_plan: planner.PassPlan, options: Dict) -> Dict[str, int]:
       'kWarps': options.get('warps') or 4,
       'kCy': 1,
       'kMinBlocks': options.get('min_blocks') or 1,
-      'kStages': options.get('stages') or 4,
+      # 4 slots of 16-byte lanes, 3 of 32-byte lanes: ~50-70 KB per CTA
+      'kStages': options.get('stages') or (4 if pass_plan.cells * max(
+          n.haoda_type.width_in_bits for n in pass_plan.nodes) <= 128 else 3),
       'kChunk': chunk,
       'kUnroll': chunk,
   }
+
+
+def _min_blocks_3d(pass_plan: planner.PassPlan) -> int:
+  """CTAs per SM to ask the compiler for: small CTAs are cheap to keep
+  resident; the estimate of the register windows keeps it from spilling."""
+  threads = pass_plan.rows // pass_plan.cy * 32
+  blocks = 4 if threads <= 128 else 2 if threads <= 256 else 1
+  window = sum(n.ring * max(1, n.haoda_type.width_in_bits // 32)
+               for n in pass_plan.nodes) * pass_plan.cells * pass_plan.cy
+  while blocks > 1 and window + 40 > 65536 // (blocks * threads):
+    blocks -= 1
+  return blocks
 
 
 def tuning_3d(pass_plan: planner.PassPlan, options: Dict) -> Dict[str, int]:
@@ -171,7 +185,7 @@ def tuning_3d(pass_plan: planner.PassPlan, options: Dict) -> Dict[str, int]:
       'kCy': pass_plan.cy,
       'kWarps': pass_plan.rows // pass_plan.cy,
       'kUnroll': unroll,
-      'kMinBlocks': options.get('min_blocks') or 1,
+      'kMinBlocks': options.get('min_blocks') or _min_blocks_3d(pass_plan),
       'kStages': stages,
       'kInDepth': in_depth,
       'kGuardBytes': guard,
@@ -263,19 +277,7 @@ def emit_program(stencil,
   schedule = planner.pass_schedule(stencil.iterate, time_block)
   variants = sorted(set(schedule), reverse=True)
   plans = {
-      tb: planner.make_pass_plan(stencil,
-                                 time_block=tb,
-                                 cells=options.get('cells'),
-                                 # measured on B200 (512^3 jacobi3d/heat3d):
-                                 # 8-row tiles are best without temporal
-                                 # blocking, 32-row tiles with it (halo share)
-                                 rows=options.get('rows') or (8 if tb == 1
-                                                              else 32),
-                                 cy=options.get('cy') or 1,
-                                 pack=False if options.get('no_pack') else None,
-                                 pipelined=False
-                                 if options.get('no_pipeline') else None)
-      for tb in variants
+      tb: planner.make_tuned_pass_plan(stencil, tb, options) for tb in variants
   }
   stages = plans[variants[0]].stages
 

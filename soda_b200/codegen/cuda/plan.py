@@ -396,6 +396,60 @@ def make_pass_plan(stencil,
                   skew=step_skew)
 
 
+def make_tuned_pass_plan(stencil, time_block: int,
+                         options: Optional[Dict] = None) -> PassPlan:
+  """``make_pass_plan`` with the launch shape chosen from the DAG.
+
+  Explicit ``options`` (cells, rows, cy, no_pack, no_pipeline) win.  The
+  defaults follow what was measured on B200:
+
+  * 2-D: 8 fp32 cells per lane instead of 4 (half the strip overlap and half
+    the shuffles per cell) while the register windows stay below ~160
+    registers; pipelined schedule.
+  * 3-D: unpacked arithmetic; as many patch rows per thread (4, 2, 1) as keep
+    the windows below ~120 registers; tile rows = 4 x the dimension-1 halo,
+    at least 8 - small CTAs, several per SM, hide the per-step barrier better
+    than one large CTA.
+  """
+  options = dict(options or {})
+  dim = stencil.dim
+  pack = False if options.get('no_pack') else None
+  pipelined = False if options.get('no_pipeline') else None
+  cells = options.get('cells')
+  probe = make_pass_plan(stencil, time_block=time_block, cells=cells,
+                         rows=256, cy=1, pack=pack, pipelined=pipelined)
+  window = sum(n.ring * max(1, n.haoda_type.width_in_bits // 32)
+               for n in probe.nodes)
+  if dim == 2:
+    if cells is None and probe.cells * 2 * window <= 160 and all(
+        t.width_in_bits == 32 for t in stencil.input_types +
+        stencil.output_types + tuple(stencil.local_types)):
+      cells = probe.cells * 2
+      try:
+        return make_pass_plan(stencil, time_block=time_block, cells=cells,
+                              pack=pack, pipelined=pipelined)
+      except util.SemanticError:
+        cells = None
+    return make_pass_plan(stencil, time_block=time_block, cells=cells,
+                          pack=pack, pipelined=pipelined)
+  if pack is None and not options.get('pack'):
+    pack = False
+  cy = options.get('cy')
+  if not cy:
+    cy = 1
+    for candidate in (4, 2):
+      if window * probe.cells * candidate <= 120:
+        cy = candidate
+        break
+  rows = options.get('rows')
+  if not rows:
+    halo = probe.halo_lo[1] + probe.halo_hi[1]
+    rows = max(8, 4 * halo)
+    rows = _round_up(rows, cy)
+  return make_pass_plan(stencil, time_block=time_block, cells=cells, rows=rows,
+                        cy=cy, pack=pack, pipelined=pipelined)
+
+
 def choose_time_block(stencil, requested: Optional[int] = None) -> int:
   """Default temporal blocking: fuse up to 4 iterations for chain programs."""
   if stencil.iterate == 1 or len(stencil.input_stmts) != len(

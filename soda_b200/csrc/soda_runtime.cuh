@@ -214,19 +214,32 @@ inline int floor_to(int value, int multiple) {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// Segments along the streamed dimension: enough CTAs for several waves, but
-// long enough that the warm-up slices (the pass's reach) stay a small fraction.
+// Segments along the streamed dimension.  CTAs run for a whole segment, so the
+// grid should fill the resident-CTA slots of the GPU in whole waves: the cost
+// model is  waves x (slices per segment + warm-up slices + fixed prologue)
+// and the segment count with the lowest cost wins (ties: fewer segments).
 inline int choose_segment(int slices, int ctas_per_slice_set, int warmup,
                           int ctas_per_sm, int requested) {
   if (requested > 0) return requested < slices ? requested : slices;
-  const int min_segment = warmup * 16 > 64 ? warmup * 16 : 64;
-  const long long target_ctas = 4LL * kNumSms * ctas_per_sm;
-  long long segments = target_ctas / (ctas_per_slice_set > 0 ? ctas_per_slice_set : 1);
-  if (segments < 1) segments = 1;
-  long long max_segments = slices / min_segment;
+  const long long tiles = ctas_per_slice_set > 0 ? ctas_per_slice_set : 1;
+  const long long slots = static_cast<long long>(kNumSms) * ctas_per_sm;
+  const int min_segment = warmup * 2 > 16 ? warmup * 2 : 16;
+  int max_segments = slices / min_segment;
   if (max_segments < 1) max_segments = 1;
-  if (segments > max_segments) segments = max_segments;
-  return ceil_div(slices, static_cast<int>(segments));
+  const int kPrologue = 6;  // barrier init, descriptor fetch, first TMA round trip
+  int best_segments = 1;
+  long long best_cost = -1;
+  for (int segments = 1; segments <= max_segments; ++segments) {
+    const int seg = ceil_div(slices, segments);
+    const int used = ceil_div(slices, seg);  // segments actually launched
+    const long long waves = (tiles * used + slots - 1) / slots;
+    const long long cost = waves * (seg + warmup + kPrologue);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_segments = used;
+    }
+  }
+  return ceil_div(slices, best_segments);
 }
 
 template <class Prog>
@@ -754,8 +767,10 @@ int soda_cuda_plan_run_host(soda_cuda_plan* plan, const void* const* in_ptrs,
   if (chunks <= 0) {
     chunks = 1;
     if (bytes >= (32LL << 20)) {
-      chunks = total / (8 * (reach > 0 ? reach : 1));
-      if (chunks > 16) chunks = 16;
+      // more chunks = shorter pipeline fill and drain; chunks of at least 4x
+      // the reach keep the redundant compute at the seams below 25 %
+      chunks = total / (4 * (reach > 0 ? reach : 1));
+      if (chunks > 32) chunks = 32;
       if (chunks < 1) chunks = 1;
     }
   }

@@ -17,23 +17,26 @@ from soda_b200.codegen.cuda import launcher  # noqa: E402
 
 
 def cases():
+  """(program, Stencil overrides, grid, time block, options); empty options =
+  the planner's defaults."""
   out = []
   out.append(('blur', {'iterate': 2}, (2000, 16384), 2, {}))
   out.append(('blur', {'iterate': 2}, (2000, 16384), 1, {}))
   out.append(('blur', {'iterate': 2}, (16000, 16384), 2, {}))
   for name in ('heat3d', 'jacobi3d'):
-    for tb in (1, 2, 4):
-      for rows in (8, 16, 32):
-        if 2 * tb >= rows:
-          continue
-        out.append((name, {'iterate': 32}, (512, 512, 512), tb, {'rows': rows}))
-  for rows in (8, 16):
-    out.append(('denoise3d', {}, (512, 512, 512), 1, {'rows': rows}))
+    for tb in (1, 2, 3):
+      out.append((name, {'iterate': 32}, (512, 512, 512), tb, {}))
+  out.append(('denoise3d', {}, (512, 512, 512), 1, {}))
   out.append(('denoise2d', {}, (8192, 8192), 1, {}))
   out.append(('seidel2d', {'iterate': 16}, (16384, 16384), 4, {}))
+  out.append(('seidel2d', {'iterate': 16}, (16384, 16384), 4, {'no_pack': True}))
   out.append(('sobel2d', {}, (16384, 16384), 1, {}))
-  for tb in (5, 6):
-    out.append(('jacobi2d', {'iterate': 60}, (16384, 16384), tb, {}))
+  out.append(('contrast', {}, (16384, 16384), 1, {}))
+  out.append(('contrast', {}, (16384, 16384), 1, {'no_pack': True}))
+  out.append(('erosion', {}, (16384, 16384), 1, {}))
+  out.append(('xcorr', {}, (16384, 16384), 1, {}))
+  for tb in (5, 6, 8):
+    out.append(('jacobi2d', {'iterate': 120}, (16384, 16384), tb, {}))
   return out
 
 
