@@ -288,7 +288,9 @@ def run_ours(args, out):
 
   # ---- end to end: host arrays through the public API (rank-local slab) ----
   e2e = None
-  if world == 1:
+  if args.no_e2e:
+    pass
+  elif world == 1:
     h_in = torch.empty((HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
     h_in.copy_(d_in)
     h_out = torch.zeros((HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
@@ -432,6 +434,8 @@ def main():
   parser.add_argument('--warmup', type=int, default=3)
   parser.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   parser.add_argument('--no-cpu-baseline', action='store_true')
+  parser.add_argument('--no-e2e', action='store_true',
+                      help='profiling runs: only the device-resident steps')
   args = parser.parse_args()
   with JsonOnlyStdout() as out:
     if args.impl == 'reference':

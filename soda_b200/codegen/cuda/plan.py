@@ -320,6 +320,31 @@ def make_pass_plan(stencil,
     node.halo_lo = tuple(halo_lo)
     node.halo_hi = tuple(halo_hi)
 
+  # The lags above are as-soon-as-possible.  A stage whose consumers all run
+  # later would only sit in a register window until then, so every stage that
+  # is not stored moves as late as its consumers allow (windows get shorter,
+  # fewer registers, fewer moves per step).  Stored nodes keep their lag: the
+  # pass latency does not grow.
+  def edge_skew(consumer: Node, prod: Node, delta) -> int:
+    if dim == 3 and delta[1] != 0 and prod.kind != 'input':
+      return 1
+    return step_skew
+
+  for node in reversed(nodes):
+    if node.kind == 'input' or node.out >= 0:
+      continue
+    latest = None
+    for consumer in nodes:
+      for prod_id, deltas in zip(consumer.prods, consumer.deltas):
+        if prod_id != node.id:
+          continue
+        for delta in deltas:
+          bound = consumer.lag - max(delta[s_dim], 0) - edge_skew(
+              consumer, node, delta)
+          latest = bound if latest is None else min(latest, bound)
+    if latest is not None and latest > node.lag:
+      node.lag = latest
+
   # register rings and shared-memory plane depths
   for node in nodes:
     ring = 1

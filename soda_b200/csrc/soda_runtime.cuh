@@ -17,7 +17,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <string>
 #include <type_traits>
@@ -76,6 +78,7 @@ struct PassArgs {
 struct PassImpl {
   soda_cuda_pass_info info;
   int (*launch)(const PassArgs&);
+  int warmup;  // slices a segment computes before its first stored slice
 };
 
 struct ProgramDesc {
@@ -214,32 +217,31 @@ inline int floor_to(int value, int multiple) {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// Segments along the streamed dimension.  CTAs run for a whole segment, so the
-// grid should fill the resident-CTA slots of the GPU in whole waves: the cost
-// model is  waves x (slices per segment + warm-up slices + fixed prologue)
-// and the segment count with the lowest cost wins (ties: fewer segments).
+// Shape of the most recent launch on this thread: CTAs per set of segments
+// (tiles across the non-streamed dimensions) and CTAs the GPU holds at once.
+struct LaunchShape {
+  int tiles;
+  int slots;
+};
+inline LaunchShape& last_launch_shape() {
+  static thread_local LaunchShape shape = {0, 0};
+  return shape;
+}
+
+// Segments along the streamed dimension, by rule: enough CTAs for about four
+// waves, but long enough that the warm-up slices stay a small fraction.  Large
+// grids replace the rule by a measurement (launch_tuned below).
 inline int choose_segment(int slices, int ctas_per_slice_set, int warmup,
                           int ctas_per_sm, int requested) {
   if (requested > 0) return requested < slices ? requested : slices;
-  const long long tiles = ctas_per_slice_set > 0 ? ctas_per_slice_set : 1;
-  const long long slots = static_cast<long long>(kNumSms) * ctas_per_sm;
-  const int min_segment = warmup * 2 > 16 ? warmup * 2 : 16;
-  int max_segments = slices / min_segment;
+  const int min_segment = warmup * 16 > 64 ? warmup * 16 : 64;
+  const long long target_ctas = 4LL * kNumSms * ctas_per_sm;
+  long long segments = target_ctas / (ctas_per_slice_set > 0 ? ctas_per_slice_set : 1);
+  if (segments < 1) segments = 1;
+  long long max_segments = slices / min_segment;
   if (max_segments < 1) max_segments = 1;
-  const int kPrologue = 6;  // barrier init, descriptor fetch, first TMA round trip
-  int best_segments = 1;
-  long long best_cost = -1;
-  for (int segments = 1; segments <= max_segments; ++segments) {
-    const int seg = ceil_div(slices, segments);
-    const int used = ceil_div(slices, seg);  // segments actually launched
-    const long long waves = (tiles * used + slots - 1) / slots;
-    const long long cost = waves * (seg + warmup + kPrologue);
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best_segments = used;
-    }
-  }
-  return ceil_div(slices, best_segments);
+  if (segments > max_segments) segments = max_segments;
+  return ceil_div(slices, static_cast<int>(segments));
 }
 
 template <class Prog>
@@ -289,6 +291,7 @@ int launch_pass_2d(const PassArgs& a) {
                               Prog::kMaxLag - Prog::kLoS, ctas_per_sm, a.segment);
   p.vec_ok = outputs_vector_aligned<Prog>(a) ? 1 : 0;
   dim3 grid(ctas_x, ceil_div(row_hi - row_lo, p.seg_rows), 1);
+  last_launch_shape() = {ctas_x, kNumSms * ctas_per_sm};
   SODA_LAUNCH(kernel, grid, Prog::kWarps * 32, S::kBytes, a.stream, p);
   launch_counter().fetch_add(1);
   SODA_CUDA_CHECK(cudaGetLastError());
@@ -343,6 +346,7 @@ int launch_pass_3d(const PassArgs& a) {
                                 Prog::kMaxLag - Prog::kLoS, ctas_per_sm, a.segment);
   p.vec_ok = outputs_vector_aligned<Prog>(a) ? 1 : 0;
   dim3 grid(tiles_x, tiles_y, ceil_div(hi[2] - lo[2], p.seg_planes));
+  last_launch_shape() = {tiles_x * tiles_y, kNumSms * ctas_per_sm};
   SODA_LAUNCH(kernel, grid, Prog::kWarps * 32, S::kBytes, a.stream, p);
   launch_counter().fetch_add(1);
   SODA_CUDA_CHECK(cudaGetLastError());
@@ -386,7 +390,137 @@ PassImpl make_pass_impl() {
   PassImpl impl;
   impl.info = pass_info_of<Prog>();
   impl.launch = &launch_pass<Prog>;
+  impl.warmup = Prog::kMaxLag - Prog::kLoS;
   return impl;
+}
+
+// ---- measured segment length ---------------------------------------------------
+// How many slices a CTA should stream depends on how the grid of CTAs fills
+// the GPU (waves, tail), on the warm-up slices per segment and on whether the
+// kernel is bound by HBM or by issue slots; the sweep in
+// profiles/r01_segment_sweep.txt shows no simple rule.  So the first launch of
+// a pass variant on a large grid times a handful of segment lengths with CUDA
+// events on the caller's stream (the pass is idempotent: same inputs, same
+// outputs) and every later launch of the same shape uses the fastest.
+// opts->segment > 0 or SODA_CUDA_AUTOTUNE=0 turn this off.
+struct TuneKey {
+  int variant, device, extent[kMaxD], lo, hi;
+  bool operator<(const TuneKey& o) const {
+    if (variant != o.variant) return variant < o.variant;
+    if (device != o.device) return device < o.device;
+    for (int d = 0; d < kMaxD; ++d)
+      if (extent[d] != o.extent[d]) return extent[d] < o.extent[d];
+    if (lo != o.lo) return lo < o.lo;
+    return hi < o.hi;
+  }
+};
+
+inline bool autotune_enabled() {
+  static const bool enabled = [] {
+    const char* env = getenv("SODA_CUDA_AUTOTUNE");
+    return env == nullptr || env[0] != '0';
+  }();
+  return enabled;
+}
+
+inline int launch_tuned(const ProgramDesc& prog, int variant, PassArgs a) {
+  const PassImpl& impl = prog.impls[variant];
+  const int dim = prog.info.dim, s_dim = dim - 1;
+  long long cells = 1;
+  for (int d = 0; d < dim; ++d) cells *= a.extent[d];
+  int lo = a.extent[s_dim], hi = 0;
+  for (int o = 0; o < prog.info.num_outputs; ++o) {
+    if (a.box_lo[o][s_dim] < lo) lo = a.box_lo[o][s_dim];
+    if (a.box_hi[o][s_dim] > hi) hi = a.box_hi[o][s_dim];
+  }
+  const int slices = hi - lo;
+  const int min_segment = impl.warmup * 2 > 8 ? impl.warmup * 2 : 8;
+  if (a.segment != 0 || !autotune_enabled() || cells < (1LL << 24) ||
+      slices < 4 * min_segment)
+    return impl.launch(a);
+
+  static std::mutex mutex;
+  static std::map<TuneKey, int> cache;
+  TuneKey key;
+  memset(&key, 0, sizeof(key));
+  key.variant = variant;
+  cudaGetDevice(&key.device);
+  for (int d = 0; d < dim; ++d) key.extent[d] = a.extent[d];
+  key.lo = lo;
+  key.hi = hi;
+  std::lock_guard<std::mutex> lock(mutex);
+  auto found = cache.find(key);
+  if (found != cache.end()) {
+    a.segment = found->second;
+    return impl.launch(a);
+  }
+
+  const long long counted = launch_counter().load();
+  int status = impl.launch(a);  // untimed: module load, attributes, cold caches
+  if (status != SODA_CUDA_OK) return status;
+  cudaEvent_t start, stop;
+  SODA_CUDA_CHECK(cudaEventCreate(&start));
+  SODA_CUDA_CHECK(cudaEventCreate(&stop));
+  auto measure = [&](int segment, float* ms) -> int {
+    PassArgs trial = a;
+    trial.segment = segment;
+    *ms = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      SODA_CUDA_CHECK(cudaEventRecord(start, a.stream));
+      int st = impl.launch(trial);
+      if (st != SODA_CUDA_OK) return st;
+      SODA_CUDA_CHECK(cudaEventRecord(stop, a.stream));
+      SODA_CUDA_CHECK(cudaEventSynchronize(stop));
+      float t = 0;
+      SODA_CUDA_CHECK(cudaEventElapsedTime(&t, start, stop));
+      if (t < *ms) *ms = t;
+    }
+    return SODA_CUDA_OK;
+  };
+  int best_segment = 0;  // 0: the rule of choose_segment()
+  float best_ms = 0;
+  status = measure(0, &best_ms);
+  // candidates: segment counts 1, 2, 3, 4, 6, 9, 13, ... plus the counts that
+  // fill the GPU's resident-CTA slots exactly k times (a grid of one full wave
+  // can beat its neighbours by 20 %), tried from many short segments to few
+  // long ones; stop once long segments have become clearly slower
+  std::vector<int> counts;
+  for (int c = 1; slices / c >= min_segment; c = c < 4 ? c + 1 : c + c / 2)
+    counts.push_back(c);
+  const LaunchShape shape = last_launch_shape();
+  if (shape.tiles > 0 && shape.slots > 0) {
+    const int waves[] = {1, 2, 3, 4, 6, 8, 12, 16};
+    for (int k : waves) {
+      const int c = k * shape.slots / shape.tiles;
+      if (c >= 1 && slices / c >= min_segment) counts.push_back(c);
+    }
+  }
+  std::sort(counts.begin(), counts.end());
+  int previous = -1, worse = 0;
+  for (size_t i = counts.size(); i-- > 0 && status == SODA_CUDA_OK;) {
+    const int segment = ceil_div(slices, counts[i]);
+    if (segment == previous) continue;
+    previous = segment;
+    float ms = 0;
+    status = measure(segment, &ms);
+    if (status != SODA_CUDA_OK) break;
+    if (ms < best_ms) {
+      best_ms = ms;
+      best_segment = segment;
+      worse = 0;
+    } else if (ms > 1.5f * best_ms && ++worse >= 2) {
+      break;
+    }
+  }
+  cudaEventDestroy(start);
+  cudaEventDestroy(stop);
+  launch_counter().store(counted + 1);  // the tuning launches repeat one pass
+  if (status != SODA_CUDA_OK) return status;
+  cache[key] = best_segment;
+  if (getenv("SODA_CUDA_VERBOSE"))
+    fprintf(stderr, "soda_cuda: variant %d slices %d -> segment %d (%.3f ms)\n",
+            variant, slices, best_segment, best_ms);
+  return SODA_CUDA_OK;
 }
 
 }  // namespace rt
@@ -515,7 +649,7 @@ inline int run_passes_window(soda_cuda_plan* plan, const void* const* d_in,
         a.box_hi[o][s_dim] = view_hi - view_lo;
       }
     }
-    int status = prog.impls[prog.schedule[pass]].launch(a);
+    int status = launch_tuned(prog, prog.schedule[pass], a);
     if (status != SODA_CUDA_OK) return status;
   }
   return SODA_CUDA_OK;
@@ -767,10 +901,11 @@ int soda_cuda_plan_run_host(soda_cuda_plan* plan, const void* const* in_ptrs,
   if (chunks <= 0) {
     chunks = 1;
     if (bytes >= (32LL << 20)) {
-      // more chunks = shorter pipeline fill and drain; chunks of at least 4x
-      // the reach keep the redundant compute at the seams below 25 %
-      chunks = total / (4 * (reach > 0 ? reach : 1));
-      if (chunks > 32) chunks = 32;
+      // chunks of at least 8x the reach: at most 12.5 % redundant compute at
+      // the seams, and windows tall enough to fill the GPU (32 chunks of the
+      // 16384^2 x 64 workload were measured slower than 16: 30.9 vs 25.8 ms)
+      chunks = total / (8 * (reach > 0 ? reach : 1));
+      if (chunks > 16) chunks = 16;
       if (chunks < 1) chunks = 1;
     }
   }
@@ -942,7 +1077,7 @@ int soda_cuda_run_pass(int32_t pass_index, const int32_t* extent,
     default_boxes(prog, ext, pass_index == prog.info.num_passes - 1, a.box_lo,
                   a.box_hi);
   }
-  return prog.impls[prog.schedule[pass_index]].launch(a);
+  return launch_tuned(prog, prog.schedule[pass_index], a);
 }
 
 }  // extern "C"

@@ -67,6 +67,14 @@ inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) {
   return cudaSuccess;
 }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) {
+  return cudaEventCreateWithFlags(e, 0);
+}
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) {
+  *ms = 1.0f;
+  return cudaSuccess;
+}
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) {
   return cudaSuccess;
