@@ -88,3 +88,29 @@ def build_library(stencil,
     print(result.stderr)
   os.replace(tmp, lib)
   return lib
+
+
+def build_layout_library(verbose: bool = False) -> str:
+  """Compiles the stream-data-layout codec (csrc/soda_layout.cu, C ABI
+  include/soda_layout.h) for sm_100a; returns the path of the .so."""
+  source = os.path.join(CSRC_DIR, 'soda_layout.cu')
+  digest = hashlib.sha1()
+  for path in (source, os.path.join(INCLUDE_DIR, 'soda_layout.h')):
+    with open(path, 'rb') as fp:
+      digest.update(fp.read())
+  os.makedirs(BUILD_DIR, exist_ok=True)
+  lib = os.path.join(BUILD_DIR,
+                     'libsoda_layout_%s.so' % digest.hexdigest()[:12])
+  if os.path.exists(lib):
+    return lib
+  tmp = '%s.%d.tmp' % (lib, os.getpid())
+  cmd = [nvcc_path()] + nvcc_flags() + ['-o', tmp, source]
+  if verbose:
+    cmd[1:1] = ['-Xptxas', '-v']
+  result = subprocess.run(cmd, capture_output=True, text=True)
+  if result.returncode != 0:
+    raise RuntimeError('nvcc failed:\n%s\n%s' % (' '.join(cmd), result.stderr))
+  if verbose:
+    print(result.stderr)
+  os.replace(tmp, lib)
+  return lib

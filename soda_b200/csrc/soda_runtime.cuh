@@ -415,6 +415,16 @@ struct TuneKey {
   }
 };
 
+// SODA_CUDA_SEGMENT=N (profiling aid): the segment length of every launch whose
+// caller did not choose one; takes the measured choice's place.
+inline int env_segment() {
+  static const int value = [] {
+    const char* env = getenv("SODA_CUDA_SEGMENT");
+    return env != nullptr ? atoi(env) : 0;
+  }();
+  return value;
+}
+
 inline bool autotune_enabled() {
   static const bool enabled = [] {
     const char* env = getenv("SODA_CUDA_AUTOTUNE");
@@ -426,6 +436,7 @@ inline bool autotune_enabled() {
 inline int launch_tuned(const ProgramDesc& prog, int variant, PassArgs a) {
   const PassImpl& impl = prog.impls[variant];
   const int dim = prog.info.dim, s_dim = dim - 1;
+  if (a.segment == 0 && env_segment() > 0) a.segment = env_segment();
   long long cells = 1;
   for (int d = 0; d < dim; ++d) cells *= a.extent[d];
   int lo = a.extent[s_dim], hi = 0;

@@ -112,3 +112,54 @@ def test_packed_fp32_eligibility():
                              pack=False).pack == 1
   text = emit.emit_program(common.stencil('jacobi2d'))
   assert 'kPack = 2' in text and 'soda::cast_to<float>' in text
+
+
+def test_stages_run_as_late_as_their_consumers_allow():
+  """ALAP: a stage nobody reads yet would only sit in a register window."""
+  p = plan.make_tuned_pass_plan(common.stencil('denoise3d'), 1)
+  by_name = {n.name: n for n in p.nodes}
+  for name in ('diff_u', 'diff_d', 'diff_l', 'diff_r', 'diff_i', 'diff_o'):
+    assert by_name[name].lag == by_name['g'].lag and by_name[name].ring == 1
+  assert by_name['r1'].lag == by_name['output'].lag and by_name['r1'].ring == 1
+  # stored nodes keep their as-soon-as-possible lag: the pass latency is the
+  # reach of the window (2 planes)
+  assert by_name['output'].lag == 2 and p.max_lag == 2
+  # every consumer still runs behind its producers
+  for node in p.nodes:
+    for prod, deltas in zip(node.prods, node.deltas):
+      for delta in deltas:
+        assert node.lag - p.nodes[prod].lag - delta[-1] >= 0
+
+
+def test_launch_shape_follows_the_dag():
+  """make_tuned_pass_plan: wide lanes / patches while the register windows
+  stay small (defaults measured on B200)."""
+  j2 = plan.make_tuned_pass_plan(common.stencil('jacobi2d', iterate=64), 6)
+  assert (j2.cells, j2.strip, j2.valid, j2.pack, j2.skew) == (8, 256, (240,), 2, 1)
+  # eight fused iterations would need 200 window registers at 8 cells: stay at 4
+  assert plan.make_tuned_pass_plan(common.stencil('jacobi2d', iterate=64),
+                                   8).cells == 4
+  j3 = plan.make_tuned_pass_plan(common.stencil('jacobi3d', iterate=32), 1)
+  assert (j3.rows, j3.cy, j3.pack, j3.skew) == (8, 4, 1, 0)
+  j3 = plan.make_tuned_pass_plan(common.stencil('jacobi3d', iterate=32), 2)
+  assert (j3.rows, j3.cy, j3.valid) == (16, 4, (120, 12))
+  d3 = plan.make_tuned_pass_plan(common.stencil('denoise3d'), 1)
+  assert (d3.rows, d3.cy) == (16, 1)  # 11 nodes: patches would spill
+  # explicit options win
+  j3 = plan.make_tuned_pass_plan(common.stencil('jacobi3d', iterate=32), 2,
+                                 {'rows': 32, 'cy': 2, 'pack': True})
+  assert (j3.rows, j3.cy, j3.pack) == (32, 2, 2)
+  text = emit.emit_program(common.stencil('jacobi3d', iterate=32), 1)
+  assert 'kCy = 4' in text and 'kWarps = 2' in text and 'kUnroll = 3' in text
+
+
+def test_patch_rows_export_only_their_edges():
+  p = plan.make_pass_plan(common.stencil('jacobi3d', iterate=32), time_block=2,
+                          rows=16, cy=4, pack=False)
+  t1, mid, out = p.nodes
+  assert mid.smem_depth == 2 and mid.smem_reach == 1
+  # with patches the dimension-1 neighbours inside the patch come from the
+  # register window, which therefore covers their (skewed) distance too
+  assert mid.ring == 3 and t1.ring == 3
+  with pytest.raises(util.SemanticError):
+    plan.make_pass_plan(common.stencil('jacobi3d'), rows=10, cy=4)

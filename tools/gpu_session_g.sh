@@ -1,0 +1,11 @@
+#!/bin/bash
+set -x
+cd "$(dirname "$0")/.."
+O=gpurun_out
+python -m pytest tests -m gpu -x -q > $O/pytest_gpu8.log 2>&1; tail -15 $O/pytest_gpu8.log
+python tools/bench_layout.py > $O/layout_bench.log 2>&1; cat $O/layout_bench.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_tb6.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $O/ncu_list_tb6.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:soda_stream2d --launch-skip 200 --launch-count 3 -o $O/prof_j2d_tb6 -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > $O/ncu_full_tb6.log 2>&1
+tail -3 $O/ncu_full_tb6.log
+ncu --set full --clock-control none --import-source on -k regex:pack_kernel -c 2 -o $O/prof_layout -f python tools/bench_layout.py > $O/ncu_layout.log 2>&1
+ls -la $O/*.ncu-rep | tail -4
