@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace soda {
 
@@ -103,17 +104,52 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const TensorMap* map,
 // left (delta < 0).  Lanes whose source falls outside the warp get their own
 // value back; the templates only ever store cells for which that cannot
 // happen.
+// Written as non-volatile inline PTX on purpose: the compiler may then merge
+// shuffles of the same register by the same distance.  A 19-tap horizontal
+// window asks for every neighbour cell once per tap and cell (152 shuffles per
+// row of 8 cells in xcorr); after merging, every source cell is shuffled once
+// (18).  The templates only shuffle in warp-uniform control flow.
+__device__ __forceinline__ unsigned shfl_bits_down(unsigned v, int delta) {
+  unsigned r;
+  asm("shfl.sync.down.b32 %0, %1, %2, 0x1f, 0xffffffff;"
+      : "=r"(r) : "r"(v), "r"(delta));
+  return r;
+}
+__device__ __forceinline__ unsigned shfl_bits_up(unsigned v, int delta) {
+  unsigned r;
+  asm("shfl.sync.up.b32 %0, %1, %2, 0x0, 0xffffffff;"
+      : "=r"(r) : "r"(v), "r"(delta));
+  return r;
+}
+
 template <int kDelta, typename T>
 __device__ __forceinline__ T shfl_rel(T v) {
   static_assert(kDelta != 0 && kDelta > -32 && kDelta < 32, "bad lane delta");
-  if constexpr (sizeof(T) < 4) {
-    int w = static_cast<int>(v);
-    w = kDelta > 0 ? __shfl_down_sync(kFullMask, w, kDelta)
-                   : __shfl_up_sync(kFullMask, w, -kDelta);
-    return static_cast<T>(w);
+  static_assert(sizeof(T) <= 8, "shuffle of wide type");
+  if constexpr (sizeof(T) == 8) {
+    unsigned long long bits;
+    memcpy(&bits, &v, 8);
+    unsigned lo = static_cast<unsigned>(bits), hi = static_cast<unsigned>(bits >> 32);
+    lo = kDelta > 0 ? shfl_bits_down(lo, kDelta) : shfl_bits_up(lo, -kDelta);
+    hi = kDelta > 0 ? shfl_bits_down(hi, kDelta) : shfl_bits_up(hi, -kDelta);
+    bits = (static_cast<unsigned long long>(hi) << 32) | lo;
+    T r;
+    memcpy(&r, &bits, 8);
+    return r;
+  } else if constexpr (sizeof(T) == 4) {
+    unsigned bits;
+    memcpy(&bits, &v, 4);
+    bits = kDelta > 0 ? shfl_bits_down(bits, kDelta) : shfl_bits_up(bits, -kDelta);
+    T r;
+    memcpy(&r, &bits, 4);
+    return r;
   } else {
-    return kDelta > 0 ? __shfl_down_sync(kFullMask, v, kDelta)
-                      : __shfl_up_sync(kFullMask, v, -kDelta);
+    // 8- and 16-bit cells travel sign- or zero-extended in a 32-bit register
+    const int w = static_cast<int>(v);
+    const unsigned bits = kDelta > 0
+        ? shfl_bits_down(static_cast<unsigned>(w), kDelta)
+        : shfl_bits_up(static_cast<unsigned>(w), -kDelta);
+    return static_cast<T>(static_cast<int>(bits));
   }
 }
 
@@ -185,8 +221,7 @@ __device__ __forceinline__ F2 f2_neg(F2 a) {
 template <int kDelta>
 __device__ __forceinline__ F2 f2_shfl(F2 v) {
   F2 r;
-  r.bits = kDelta > 0 ? __shfl_down_sync(kFullMask, v.bits, kDelta)
-                      : __shfl_up_sync(kFullMask, v.bits, -kDelta);
+  r.bits = shfl_rel<kDelta>(v.bits);
   return r;
 }
 

@@ -589,8 +589,16 @@ __global__ void __launch_bounds__(Prog::kWarps * 32, Prog::kMinBlocks)
     mbar_wait(&full[slot], parity);
     ctx.slot_base = slots + slot * S::kSlotBytes;
     const int t0 = t_begin + chunk * kChunk;
+    if constexpr (Prog::kRowUnroll > 1) {
 #pragma unroll
-    for (int r = 0; r < kChunk; ++r) step_nodes_2d<Prog>(ctx, t0 + r, r);
+      for (int r = 0; r < kChunk; ++r) step_nodes_2d<Prog>(ctx, t0 + r, r);
+    } else {
+      // deep windows (contrast: 17 rows of 197 taps): one copy of the step body,
+      // the window is shifted; unrolling would spill (measured: 12 KB of spill
+      // loads per thread and 2x the time)
+#pragma unroll 1
+      for (int r = 0; r < kChunk; ++r) step_nodes_2d<Prog>(ctx, t0 + r, r);
+    }
     warp_sync();  // every lane is done reading the slot
     if (ctx.lane == 0 && chunk + kStages < num_chunks) {
       mbar_arrive_expect_tx(&full[slot], S::kSlotBytes);

@@ -34,7 +34,9 @@ def cases():
   out.append(('contrast', {}, (16384, 16384), 1, {}))
   out.append(('contrast', {}, (16384, 16384), 1, {'no_pack': True}))
   out.append(('erosion', {}, (16384, 16384), 1, {}))
+  out.append(('erosion', {}, (16384, 16384), 1, {'row_unroll': 6}))
   out.append(('xcorr', {}, (16384, 16384), 1, {}))
+  out.append(('xcorr', {}, (16384, 16384), 1, {'row_unroll': 6}))
   for tb in (5, 6, 8):
     out.append(('jacobi2d', {'iterate': 120}, (16384, 16384), tb, {}))
   return out

@@ -29,7 +29,7 @@ from soda_b200.codegen.cuda import launcher, multi_gpu  # noqa: E402
 
 W = H = int(os.environ.get('C5_SIZE', '65536'))
 ITERATE = int(os.environ.get('C5_ITERATE', '256'))
-TB = int(os.environ.get('C5_TIME_BLOCK', '5'))
+TB = int(os.environ.get('C5_TIME_BLOCK', '6'))
 
 
 def main():
