@@ -109,6 +109,12 @@ typedef struct soda_cuda_program_info {
   int32_t num_passes;
   int32_t strict_fp;            /* 1: compiled with --fmad=false (bit-exact vs g++) */
   int32_t algorithmic_bytes_per_cell_per_pass;
+  /* `param` arrays of the program (reference: src/soda/grammar.py ParamStmt;
+   * soda::app::<app> takes them after the tensors, frt/host.py:73-79) */
+  int32_t num_params;
+  const char* param_names[SODA_CUDA_MAX_TENSORS];
+  int32_t param_dtypes[SODA_CUDA_MAX_TENSORS];
+  int32_t param_elems[SODA_CUDA_MAX_TENSORS];   /* product of the declared sizes */
 } soda_cuda_program_info;
 
 typedef struct soda_cuda_plan soda_cuda_plan;   /* opaque */
@@ -156,6 +162,16 @@ SODA_CUDA_API int soda_cuda_run_pass(int32_t pass_index, const int32_t* extent,
                        const int32_t (*box_lo)[SODA_CUDA_MAX_DIM],
                        const int32_t (*box_hi)[SODA_CUDA_MAX_DIM],
                        const soda_cuda_opts* opts);
+
+/* Values of `param` array `index` (dense, row-major over the declared sizes,
+ * param_elems[index] elements of host memory).  They are copied into the
+ * constant memory of the device `opts->device` (default: the current device)
+ * and used by every later launch of this library on that device; set them
+ * before launching.  The reference passes params to soda::app::<app> with the
+ * same (ptr, extent, stride, min) quadruple as tensors (frt/host.py:73-79);
+ * soda_cuda_<app> does too and calls this function. */
+SODA_CUDA_API int soda_cuda_set_param(int32_t index, const void* values,
+                                      const soda_cuda_opts* opts);
 
 /* Number of kernel launches issued by this library since it was loaded. */
 SODA_CUDA_API int64_t soda_cuda_launch_count(void);

@@ -186,8 +186,13 @@ class _Evaluator:
 
 
 def run(stencil, inputs: Dict[str, np.ndarray],
-        keep_intermediates: bool = False) -> Dict[str, np.ndarray]:
+        keep_intermediates: bool = False,
+        params: Dict[str, np.ndarray] = None) -> Dict[str, np.ndarray]:
   """Evaluates the whole ``iterate``-unrolled chain on ``inputs``.
+
+  ``params``: {param name: array of the declared size}; a reference ``p(i, j)``
+  is the constant ``p[i][j]`` (reference:
+  src/soda/codegen/frt/host.py:580-586).
 
   Returns {output name: array}; cells outside an output's valid box are zero
   (the reference leaves them untouched; compare only inside
@@ -222,6 +227,8 @@ def run(stencil, inputs: Dict[str, np.ndarray],
       st_idx = tensor.st_idx
 
       def load(ref, tensor=tensor, box=box, st_idx=st_idx):
+        if ref.name in stencil.param_names:
+          return np.asarray(params[ref.name])[tuple(ref.idx)]
         delta = tuple(a - b for a, b in zip(ref.idx, st_idx))
         index = tuple(
             slice(box[d][0] + delta[d], box[d][1] + delta[d])
@@ -266,6 +273,17 @@ def reference_inputs(stencil, extent: Sequence[int],
     else:
       grids = np.indices(shape).sum(axis=0)
       result[stmt.name] = grids.astype(dtype)
+  return result
+
+
+def reference_params(stencil) -> Dict[str, np.ndarray]:
+  """Params as the reference's test main fills them: ``p[x][y] = x + y``
+  (reference: src/soda/codegen/frt/host.py:530-543)."""
+  result = {}
+  for stmt in stencil.param_stmts:
+    shape = tuple(int(x) for x in stmt.size)
+    result[stmt.name] = np.indices(shape).sum(axis=0).astype(
+        np_dtype(stmt.haoda_type))
   return result
 
 

@@ -76,12 +76,25 @@ class _FunctorPrinter(ir.CPrinter):
     return super().__call__(node)
 
 
-def _functor(desc: planner.StageDesc, dim: int) -> List[str]:
+def _functor(desc: planner.StageDesc, dim: int,
+             param_sizes: Optional[Dict[str, List[int]]] = None) -> List[str]:
   stmt = desc.stmt
   slots = {name: k for k, name in enumerate(desc.slots)}
   st_idx = stmt.ref.idx
+  param_sizes = param_sizes or {}
 
   def ref_printer(ref: ir.Ref) -> str:
+    if ref.name in param_sizes:
+      # p(i, j) is the constant p[i][j]
+      # (reference: src/soda/codegen/frt/host.py:580-586)
+      sizes = param_sizes[ref.name]
+      if len(ref.idx) != len(sizes) or any(
+          not 0 <= i < n for i, n in zip(ref.idx, sizes)):
+        raise util.SemanticError('param reference %s is out of range' % ref)
+      linear = 0
+      for index, size in zip(ref.idx, sizes):
+        linear = linear * size + index
+      return 'soda_gen::param_%s[%d]' % (ref.name, linear)
     delta = [a - b for a, b in zip(ref.idx, st_idx)]
     dx = delta[0]
     dy = delta[1] if dim == 3 else 0
@@ -296,11 +309,25 @@ def emit_program(stencil,
       '#include <math.h>',
       '#include "soda_stream.cuh"',
       _HELPERS,
+  ]
+  # `param` arrays live in constant memory: every lane reads the same element
+  param_sizes = {s.name: [int(x) for x in s.size] for s in stencil.param_stmts}
+  if param_sizes:
+    lines.append('namespace soda_gen {')
+    for stmt in stencil.param_stmts:
+      elems = 1
+      for n in param_sizes[stmt.name]:
+        elems *= n
+      lines.append('// %s' % stmt)
+      lines.append('SODA_CONSTANT %s param_%s[%d];' %
+                   (stmt.haoda_type.c_type, stmt.name, elems))
+    lines.append('}  // namespace soda_gen')
+  lines += [
       'namespace soda_gen {',
       'template <int F> struct Stage;',
   ]
   for desc in stages:
-    lines.extend(_functor(desc, dim))
+    lines.extend(_functor(desc, dim, param_sizes))
   lines.append('}  // namespace soda_gen')
   lines.append('')
   lines.append('namespace soda_gen {')
@@ -352,6 +379,19 @@ def emit_program(stencil,
                (0 if options.get('fast_fp') else 1))
   lines.append('    d.info.algorithmic_bytes_per_cell_per_pass = %d;' %
                bytes_per_cell)
+  lines.append('    d.info.num_params = %d;' % len(stencil.param_stmts))
+  for k, stmt in enumerate(stencil.param_stmts):
+    elems = 1
+    for n in param_sizes[stmt.name]:
+      elems *= n
+    lines.append('    d.info.param_names[%d] = "%s";' % (k, stmt.name))
+    lines.append('    d.info.param_dtypes[%d] = %s;' %
+                 (k, DTYPE_CODES[str(stmt.haoda_type)]))
+    lines.append('    d.info.param_elems[%d] = %d;' % (k, elems))
+    lines.append('    d.param_symbol[%d] = &soda_gen::param_%s;' %
+                 (k, stmt.name))
+    lines.append('    d.param_bytes[%d] = %d;' %
+                 (k, elems * (stmt.haoda_type.width_in_bits // 8)))
   lines.append('    d.impls = impls;')
   lines.append('    d.num_impls = %d;' % len(variants))
   lines.append('    d.schedule = schedule;')
@@ -369,6 +409,10 @@ def emit_program(stencil,
                   for what in ('extent', 'stride', 'min'))
   for stmt in stencil.output_stmts:
     params.append('%s* var_%s_ptr' % (stmt.haoda_type.c_type, stmt.name))
+    params.extend('const int32_t* var_%s_%s' % (stmt.name, what)
+                  for what in ('extent', 'stride', 'min'))
+  for stmt in stencil.param_stmts:  # after the tensors, src/.../host.py:73
+    params.append('const %s* var_%s_ptr' % (stmt.haoda_type.c_type, stmt.name))
     params.extend('const int32_t* var_%s_%s' % (stmt.name, what)
                   for what in ('extent', 'stride', 'min'))
   params.append('const soda_cuda_opts* opts')
@@ -390,6 +434,14 @@ def emit_program(stencil,
                  (stmt.name, first))
     lines.append('        return soda::rt::fail(SODA_CUDA_BAD_ARGUMENT, '
                  '"all tensors must share one extent");')
+  for k, stmt in enumerate(stencil.param_stmts):
+    # params are small dense arrays (the reference declares them as C arrays,
+    # src/soda/codegen/frt/host.py:497-500); extent / stride / min are accepted
+    # for signature compatibility
+    for what in ('extent', 'stride', 'min'):
+      lines.append('  (void)var_%s_%s;' % (stmt.name, what))
+    lines.append('  { int status = soda_cuda_set_param(%d, var_%s_ptr, opts); '
+                 'if (status != SODA_CUDA_OK) return status; }' % (k, stmt.name))
   lines.append('  const void* in_ptrs[] = {%s};' %
                ', '.join('var_%s_ptr' % s.name for s in stencil.input_stmts))
   lines.append('  const int32_t* in_strides[] = {%s};' %

@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     'soda_cuda_plan_run_device',
     'soda_cuda_run_pass',
     'soda_cuda_launch_count',
+    'soda_cuda_set_param',
 )
 
 
@@ -81,6 +82,10 @@ class ProgramInfo(ctypes.Structure):
       ('num_passes', ctypes.c_int32),
       ('strict_fp', ctypes.c_int32),
       ('algorithmic_bytes_per_cell_per_pass', ctypes.c_int32),
+      ('num_params', ctypes.c_int32),
+      ('param_names', ctypes.c_char_p * MAX_TENSORS),
+      ('param_dtypes', ctypes.c_int32 * MAX_TENSORS),
+      ('param_elems', ctypes.c_int32 * MAX_TENSORS),
   ]
 
 
@@ -131,6 +136,12 @@ class CudaProgram:
                          for i in range(info.num_inputs)]
     self.output_dtypes = [np.dtype(DTYPES[info.output_dtypes[i]])
                           for i in range(info.num_outputs)]
+    self.param_names = [info.param_names[i].decode()
+                        for i in range(info.num_params)]
+    self.param_dtypes = [np.dtype(DTYPES[info.param_dtypes[i]])
+                         for i in range(info.num_params)]
+    self.param_elems = [int(info.param_elems[i])
+                        for i in range(info.num_params)]
     self.num_passes = info.num_passes
     self.bytes_per_cell_per_pass = info.algorithmic_bytes_per_cell_per_pass
     self.app_entry = getattr(self.lib, 'soda_cuda_' + self.app_name)
@@ -165,15 +176,41 @@ class CudaProgram:
       raise ValueError('array strides must be multiples of the element size')
     return tuple(s // array.itemsize for s in array.strides[::-1])
 
+  # -- params ------------------------------------------------------------------
+  def _param_array(self, index: int, values) -> np.ndarray:
+    array = np.ascontiguousarray(values, dtype=self.param_dtypes[index])
+    if array.size != self.param_elems[index]:
+      raise ValueError('param %s has %d elements, got %d' %
+                       (self.param_names[index], self.param_elems[index],
+                        array.size))
+    return array
+
+  def set_params(self, params: Dict[str, np.ndarray],
+                 opts: Optional[Opts] = None) -> None:
+    """Values of the program's ``param`` arrays (used by every later launch
+    on the device of ``opts``)."""
+    for index, name in enumerate(self.param_names):
+      array = self._param_array(index, params[name])
+      self._check(self.lib.soda_cuda_set_param(
+          index, ctypes.c_void_p(array.ctypes.data),
+          ctypes.byref(opts) if opts is not None else None))
+
   # -- host arrays -------------------------------------------------------------
   def run_host(self,
                inputs: Dict[str, np.ndarray],
                outputs: Optional[Dict[str, np.ndarray]] = None,
                opts: Optional[Opts] = None,
-               use_app_entry: bool = True) -> Dict[str, np.ndarray]:
+               use_app_entry: bool = True,
+               params: Optional[Dict[str, np.ndarray]] = None
+               ) -> Dict[str, np.ndarray]:
     """Runs the program on NumPy arrays (shape ``extent[::-1]``, dimension 0
     contiguous).  Only the valid interior of each output is written; pass
-    ``outputs`` to see that the rest is left untouched."""
+    ``outputs`` to see that the rest is left untouched.  ``params``: values of
+    the program's ``param`` arrays (required when it declares any and they were
+    not set with ``set_params``)."""
+    if self.param_names and params is None and use_app_entry:
+      raise ValueError('program %s needs params %s' %
+                       (self.app_name, self.param_names))
     ins = []
     for name, dtype in zip(self.input_names, self.input_dtypes):
       array = inputs[name]
@@ -209,9 +246,21 @@ class CudaProgram:
       args = []
       for array, stride in zip(ins + outs, strides):
         args += [ctypes.c_void_p(array.ctypes.data), c_extent, stride, zeros]
+      keep = []
+      for index, name in enumerate(self.param_names):
+        array = self._param_array(index, params[name])
+        keep.append(array)
+        shape = list(np.shape(params[name]))[::-1] or [array.size]
+        p_extent = (ctypes.c_int32 * len(shape))(*shape)
+        p_zero = (ctypes.c_int32 * len(shape))(*([0] * len(shape)))
+        p_stride = (ctypes.c_int32 * len(shape))(
+            *[int(np.prod(shape[:d])) for d in range(len(shape))])
+        args += [ctypes.c_void_p(array.ctypes.data), p_extent, p_stride, p_zero]
       args.append(opts_ref)
       self._check(self.app_entry(*args))
     else:
+      if params is not None:
+        self.set_params(params, opts)
       n_in, n_out = len(ins), len(outs)
       in_ptrs = (ctypes.c_void_p * n_in)(*[a.ctypes.data for a in ins])
       out_ptrs = (ctypes.c_void_p * n_out)(*[a.ctypes.data for a in outs])

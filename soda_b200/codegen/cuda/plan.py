@@ -103,7 +103,7 @@ def stage_descs(stencil) -> List[StageDesc]:
   deps = {}
   for s in stmts:
     loaded = set()
-    for ref in _stmt_loads(s):
+    for ref in _stmt_loads(s, stencil.param_names):
       if ref.name in names:
         loaded.add(ref.name)
     deps[s.name] = loaded
@@ -123,18 +123,21 @@ def stage_descs(stencil) -> List[StageDesc]:
   result = []
   for i, s in enumerate(order):
     slots: List[str] = []
-    for ref in _stmt_loads(s):
+    for ref in _stmt_loads(s, stencil.param_names):
       if ref.name not in slots:
         slots.append(ref.name)
     result.append(StageDesc(index=i, stmt=s, slots=slots))
   return result
 
 
-def _stmt_loads(stmt) -> Tuple[ir.Ref, ...]:
+def _stmt_loads(stmt, params: Sequence[str] = ()) -> Tuple[ir.Ref, ...]:
+  """Tensor loads of a statement; references to ``param`` arrays are constants,
+  not loads (reference: src/soda/core.py:292-293)."""
   loads: Tuple[ir.Ref, ...] = ()
   for let in stmt.let:
     loads += visitor.get_load_tuple(let)
-  return loads + visitor.get_load_tuple(stmt.expr)
+  loads += visitor.get_load_tuple(stmt.expr)
+  return tuple(ref for ref in loads if ref.name not in params)
 
 
 def _round_up(value: int, multiple: int) -> int:
@@ -210,9 +213,10 @@ def make_pass_plan(stencil,
   per DAG level and no registers: a window of depth ``d`` still holds the
   ``d`` slices a consumer reads, they are just one step older.
   """
-  if stencil.param_stmts:
-    raise util.SemanticError('param statements are not supported by the CUDA '
-                             'backend')
+  for stmt in stencil.param_stmts:
+    if not stmt.haoda_type.is_executable or not stmt.size:
+      raise util.SemanticError('param %s: unsupported type or shape' %
+                               stmt.name)
   dim = stencil.dim
   if dim not in (2, 3):
     raise util.SemanticError(
@@ -275,7 +279,7 @@ def make_pass_plan(stencil,
                   if stencil.iterate > iteration else stmt.name,
                   haoda_type=stmt.haoda_type)
       by_slot: Dict[str, List[Tuple[int, ...]]] = {n: [] for n in desc.slots}
-      for ref in _stmt_loads(stmt):
+      for ref in _stmt_loads(stmt, stencil.param_names):
         delta = tuple(a - b for a, b in zip(ref.idx, stmt.ref.idx))
         if delta not in by_slot[ref.name]:
           by_slot[ref.name].append(delta)

@@ -8,6 +8,9 @@
 #include <stdint.h>
 #include <string.h>
 
+// `param` arrays of a program (generated code) live in constant memory
+#define SODA_CONSTANT __constant__
+
 namespace soda {
 
 constexpr unsigned kFullMask = 0xffffffffu;

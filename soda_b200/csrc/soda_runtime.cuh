@@ -88,6 +88,9 @@ struct ProgramDesc {
   const PassImpl* impls;
   int num_impls;
   const int* schedule;  // impl index of every pass
+  // `param` arrays: constant-memory symbols of the generated file
+  const void* param_symbol[kMaxT];
+  int param_bytes[kMaxT];
 };
 
 // ---- TMA descriptors ----------------------------------------------------------
@@ -777,6 +780,26 @@ int soda_cuda_get_pass_info(int32_t pass_index, soda_cuda_pass_info* info) {
 const char* soda_cuda_last_error(void) { return soda::rt::last_error().c_str(); }
 
 int64_t soda_cuda_launch_count(void) { return soda::rt::launch_counter().load(); }
+
+int soda_cuda_set_param(int32_t index, const void* values,
+                        const soda_cuda_opts* opts) {
+  using namespace soda::rt;
+  const ProgramDesc& prog = soda_program();
+  if (index < 0 || index >= prog.info.num_params)
+    return fail(SODA_CUDA_BAD_ARGUMENT, "bad param index");
+  if (values == nullptr) return fail(SODA_CUDA_BAD_ARGUMENT, "param values are NULL");
+  DeviceGuard guard;
+  int status = guard.enter(opts ? opts->device : -1);
+  if (status != SODA_CUDA_OK) return status;
+  cudaStream_t stream = opts ? static_cast<cudaStream_t>(opts->stream) : nullptr;
+  // ordered after the launches already queued on the stream, visible to the
+  // ones queued afterwards
+  SODA_CUDA_CHECK(cudaMemcpyToSymbolAsync(prog.param_symbol[index], values,
+                                          prog.param_bytes[index], 0,
+                                          cudaMemcpyHostToDevice, stream));
+  SODA_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return SODA_CUDA_OK;
+}
 
 int soda_cuda_plan_create(const int32_t* extent, const soda_cuda_opts* opts,
                           soda_cuda_plan** out) {

@@ -78,7 +78,24 @@ def assert_matches_oracle(st, extent, got, want, sentinel=None):
           '%s: cells outside the valid box were written' % name
 
 
-def oracle_outputs(st, inputs, use_cpp=True):
+def make_params(st, seed=0, pattern='random'):
+  """``param`` arrays: the reference test main's ``p[x][y] = x + y`` or seeded
+  random values."""
+  if pattern == 'reference':
+    return golden.reference_params(st)
+  rng = np.random.default_rng(seed + 1000)
+  result = {}
+  for stmt in st.param_stmts:
+    shape = tuple(int(x) for x in stmt.size)
+    dtype = golden.np_dtype(stmt.haoda_type)
+    if stmt.haoda_type.is_float:
+      result[stmt.name] = (rng.random(shape) - 0.5).astype(dtype)
+    else:
+      result[stmt.name] = rng.integers(-4, 5, shape).astype(dtype)
+  return result
+
+
+def oracle_outputs(st, inputs, use_cpp=True, params=None):
   if use_cpp:
-    return emit_cpp.Oracle(st).run(inputs)
-  return golden.run(st, inputs)
+    return emit_cpp.Oracle(st).run(inputs, params=params)
+  return golden.run(st, inputs, params=params)

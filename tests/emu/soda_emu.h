@@ -39,6 +39,8 @@ using std::min;
 enum cudaError_t { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorUnknown = 999 };
 typedef void* cudaStream_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2 };
+// `param` arrays: plain host memory in the emulation
+#define SODA_CONSTANT static
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0 };
 constexpr unsigned long long cudaEnableDefault = 0;
@@ -67,6 +69,12 @@ inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) {
   return cudaSuccess;
 }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaMemcpyToSymbolAsync(const void* symbol, const void* src,
+                                           size_t bytes, size_t offset,
+                                           cudaMemcpyKind, cudaStream_t) {
+  memcpy(static_cast<char*>(const_cast<void*>(symbol)) + offset, src, bytes);
+  return cudaSuccess;
+}
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) {
   return cudaEventCreateWithFlags(e, 0);
 }

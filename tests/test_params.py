@@ -1,0 +1,103 @@
+"""`param` statements through the whole stack.
+
+The reference declares params as constant arrays next to the tensors
+(src/soda/grammar.py ParamStmt), passes them to soda::app::<app> after the
+tensors with the same (ptr, extent, stride, min) quadruple
+(src/soda/codegen/frt/host.py:73-79), fills them with ``p[x][y] = x + y`` in
+its test main (:530-543) and evaluates a reference ``p(i, j)`` as the constant
+``p[i][j]`` (:580-586).  None of its tests/src programs uses one, so the two
+programs here live in tests/src_extra."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import emit_cpp, golden
+from soda_b200 import sodac, util
+from soda_b200.codegen.cuda import emit, launcher, plan
+from tests import common
+from tests.emu import build_emu
+
+EXTRA = os.path.join(common.ROOT, 'tests', 'src_extra')
+CASES = [('conv2d_param', (300, 41), {}),
+         ('conv2d_param', (200, 30), {'options': {'no_pack': True}}),
+         ('scale3d_param', (150, 21, 9), {})]
+
+
+def stencil(name, **overrides):
+  with open(os.path.join(EXTRA, name + '.soda')) as fp:
+    return sodac.compile_source(fp.read(), **overrides)
+
+
+def test_front_end_round_trip_and_plan():
+  st = stencil('conv2d_param')
+  assert st.param_names == ('weight', 'bias')
+  assert 'param float: weight[3][3]' in str(st)
+  again = sodac.compile_source(str(st))
+  assert str(again) == str(st)
+  p = plan.make_tuned_pass_plan(st, 1)
+  # params are constants, not loads: the DAG only has the tensors
+  assert [n.name for n in p.nodes] == ['img', 'acc', 'out']
+  text = emit.emit_program(st)
+  assert 'SODA_CONSTANT float param_weight[9];' in text
+  assert 'soda_gen::param_weight[5]' in text and 'soda_gen::param_bias[0]' in text
+  # soda::app::<app> takes the params after the tensors
+  assert text.index('var_out_ptr') < text.index('const float* var_weight_ptr')
+
+
+def test_out_of_range_param_reference_is_rejected():
+  text = open(os.path.join(EXTRA, 'conv2d_param.soda')).read().replace(
+      'weight(2, 2)', 'weight(3, 0)')
+  with pytest.raises(util.SemanticError):
+    emit.emit_program(sodac.compile_source(text))
+
+
+@pytest.mark.parametrize('name,extent,kwargs', CASES)
+def test_oracles_agree_on_param_programs(name, extent, kwargs):
+  st = stencil(name)
+  inputs = common.make_inputs(st, extent, seed=2)
+  for pattern in ('reference', 'random'):
+    params = common.make_params(st, seed=3, pattern=pattern)
+    a = golden.run(st, inputs, params=params)
+    b = emit_cpp.Oracle(st).run(inputs, params=params)
+    for out in st.output_names:
+      index = common.box_index(st.valid_box(out, extent))
+      assert np.array_equal(a[out][index].view(np.uint32),
+                            b[out][index].view(np.uint32))
+
+
+def _run(prog, st, extent, seed=5):
+  inputs = common.make_inputs(st, extent, seed=seed)
+  params = common.make_params(st, seed=seed)
+  outputs = {n: np.full(extent[::-1], 77, dtype=d)
+             for n, d in zip(prog.output_names, prog.output_dtypes)}
+  prog.run_host(inputs, outputs, params=params)
+  want = common.oracle_outputs(st, inputs, params=params)
+  common.assert_matches_oracle(st, extent, outputs, want, sentinel=77)
+  # new values replace the old ones
+  params2 = {k: v + 1 for k, v in params.items()}
+  prog.run_host(inputs, outputs, params=params2)
+  want2 = common.oracle_outputs(st, inputs, params=params2)
+  common.assert_matches_oracle(st, extent, outputs, want2, sentinel=77)
+
+
+@pytest.mark.parametrize('name,extent,kwargs', CASES)
+def test_param_programs_under_emulation(name, extent, kwargs):
+  st = stencil(name)
+  small = tuple(max(8, e // 4) for e in extent)
+  prog = launcher.CudaProgram(build_emu.build_emu_library(st, **kwargs))
+  assert prog.param_names == list(st.param_names)
+  _run(prog, st, small)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,extent,kwargs', CASES)
+def test_param_programs_on_gpu(name, extent, kwargs):
+  from soda_b200.codegen import cuda as cuda_backend
+  st = stencil(name)
+  prog = cuda_backend.compile_stencil(st, **kwargs)
+  before = prog.launch_count()
+  _run(prog, st, extent)
+  assert prog.launch_count() > before
+  with pytest.raises(ValueError):
+    prog.run_host(common.make_inputs(st, extent))  # params missing
