@@ -131,7 +131,7 @@ def _lcm(values: Sequence[int]) -> int:
 def tuning_2d(pass_plan: planner.PassPlan, options: Dict) -> Dict[str, int]:
   """Launch-shape constants of the 2-D template."""
   rings = sorted({n.ring for n in pass_plan.nodes})
-  taps = max([1] + [sum(len(d) for d in n.deltas) for n in pass_plan.nodes])
+  taps = sum(sum(len(d) for d in n.deltas) for n in pass_plan.nodes)
   period = _lcm([r for r in rings if r <= 4]) or 1
   chunk = options.get('chunk') or 6
   # a chunk that is a multiple of the window depths lets the unrolled step
@@ -148,9 +148,10 @@ def tuning_2d(pass_plan: planner.PassPlan, options: Dict) -> Dict[str, int]:
       'kChunk': chunk,
       'kUnroll': chunk,
       # the rows of a chunk are unrolled (window rotation by renaming) unless
-      # the windows are deep or the statements huge
-      'kRowUnroll': options.get('row_unroll') or
-                    (1 if max(rings) > 8 or taps > 64 else chunk),
+      # the pass is huge (contrast: 197 taps - unrolled it spills 12 KB per
+      # thread; erosion / xcorr with 19-deep windows but 19 taps are 1.5x
+      # faster unrolled)
+      'kRowUnroll': options.get('row_unroll') or (1 if taps > 100 else chunk),
   }
 
 

@@ -33,6 +33,7 @@ int fail(int status, const std::string& message) {
 
 struct Geometry {
   int dim, banks;
+  int bank_shift;  // log2(banks) when banks is a power of two, else -1
   int extent[3], tile_size[3], stencil_dim[3], window_offset[3], window_dim[3];
   int tile_count[3], tile_stride[3];
   long long stride[3];
@@ -99,8 +100,15 @@ __device__ __forceinline__ long long original_offset(const Geometry& g,
 struct BankCursor {
   int bank;
   long long pos;
-  __device__ __forceinline__ BankCursor(const Geometry& g, long long t)
-      : bank(static_cast<int>(t % g.banks)), pos(t / g.banks) {}
+  __device__ __forceinline__ BankCursor(const Geometry& g, long long t) {
+    if (g.bank_shift >= 0) {
+      bank = static_cast<int>(t & (g.banks - 1));
+      pos = t >> g.bank_shift;
+    } else {
+      bank = static_cast<int>(t % g.banks);
+      pos = t / g.banks;
+    }
+  }
   __device__ __forceinline__ void next(const Geometry& g) {
     if (++bank == g.banks) {
       bank = 0;
@@ -215,20 +223,22 @@ __global__ void __launch_bounds__(kThreads)
     dst = y * g.stride[1];
   }
   T* out = dense + dst;
-  const long long row_base = in_tile + g.stencil_offset;
-  const bool one_bank = g.banks == 1;
+  // stream offset of column c0 of the current tile is base + c0
+  long long base = (tile + idx0) * g.aligned + in_tile + g.stencil_offset;
+  int limit = actual_tile_size(g, 0, idx0) - cut0;  // first column not stored
 #pragma unroll
   for (int k = 0; k < kRun; ++k, x += 32, c0 += 32) {
     if (x >= x_hi) return;
     while (c0 >= g.tile_stride[0] + lo0 && idx0 < last) {
       ++idx0;  // the valid range of the next tile starts here
       c0 -= g.tile_stride[0];
+      base += g.aligned;
+      limit = actual_tile_size(g, 0, idx0) - cut0;
     }
     // a column between two tiles' valid ranges is not stored by the reference
-    if (c0 >= actual_tile_size(g, 0, idx0) - cut0) continue;
-    const long long t = (tile + idx0) * g.aligned + row_base + c0;
-    out[x] = one_bank ? static_cast<const T*>(g.bank[0])[t]
-                      : static_cast<const T*>(g.bank[t % g.banks])[t / g.banks];
+    if (c0 >= limit) continue;
+    const BankCursor in(g, base + c0);
+    out[x] = static_cast<const T*>(g.bank[in.bank])[in.pos];
   }
 }
 
@@ -249,6 +259,9 @@ int make_geometry(const soda_stream_layout* l, Geometry* g) {
   memset(g, 0, sizeof(*g));
   g->dim = l->dim;
   g->banks = l->banks;
+  g->bank_shift = -1;
+  for (int k = 0; k < 6; ++k)
+    if ((1 << k) == l->banks) g->bank_shift = k;
   g->tiles_total = 1;
   for (int d = 0; d < l->dim; ++d) {
     if (l->extent[d] <= 0)

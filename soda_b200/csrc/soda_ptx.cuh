@@ -147,12 +147,15 @@ __device__ __forceinline__ T shfl_rel(T v) {
     memcpy(&r, &bits, 4);
     return r;
   } else {
-    // 8- and 16-bit cells travel sign- or zero-extended in a 32-bit register
+    // 8- and 16-bit cells travel sign- or zero-extended in a 32-bit register;
+    // what arrives is again such a value (tell the compiler, it cannot see
+    // through the shuffle and would re-normalise)
     const int w = static_cast<int>(v);
-    const unsigned bits = kDelta > 0
-        ? shfl_bits_down(static_cast<unsigned>(w), kDelta)
-        : shfl_bits_up(static_cast<unsigned>(w), -kDelta);
-    return static_cast<T>(static_cast<int>(bits));
+    const int r = static_cast<int>(
+        kDelta > 0 ? shfl_bits_down(static_cast<unsigned>(w), kDelta)
+                   : shfl_bits_up(static_cast<unsigned>(w), -kDelta));
+    __builtin_assume(r == static_cast<int>(static_cast<T>(r)));
+    return static_cast<T>(r);
   }
 }
 

@@ -105,10 +105,21 @@ __device__ __forceinline__ auto cast_to(From v) {
   }
 }
 
+// 8- and 16-bit integer cells are kept in 32-bit registers that hold the
+// converted value (zero- or sign-extended), so that the conversion to the
+// tensor's type is paid once, where the cell is produced, instead of as a mask
+// or sign extension at every use (ptxas keeps 16-bit values in 32-bit
+// registers and re-normalises them whenever it cannot see the upper bits).
+template <typename T>
+using CarrierOf = typename std::conditional<
+    std::is_integral<T>::value && sizeof(T) < 4,
+    typename std::conditional<std::is_signed<T>::value, int, unsigned>::type,
+    T>::type;
+
 // A lane owns kCells cells = kUnits units of kPack cells.
 template <class Prog, int N>
-using UnitOf = typename std::conditional<Prog::kPack == 2, F2,
-                                         typename Prog::template T<N>>::type;
+using UnitOf = typename std::conditional<
+    Prog::kPack == 2, F2, CarrierOf<typename Prog::template T<N>>>::type;
 template <class Prog>
 constexpr int kUnitsOf = Prog::kCells / Prog::kPack;
 
@@ -136,7 +147,7 @@ __device__ __forceinline__ void cells_from_units(
       cells[u] = f2_lo(units[u]);
       cells[u + kUnitsOf<Prog>] = f2_hi(units[u]);
     } else {
-      cells[u] = units[u];
+      cells[u] = static_cast<typename Prog::template T<N>>(units[u]);
     }
   }
 }
@@ -256,7 +267,8 @@ struct Access {
       const F2 unit = ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal % kH];
       v = kLocal >= kH ? f2_hi(unit) : f2_lo(unit);
     } else {
-      v = ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal];
+      v = static_cast<typename Prog::template T<P>>(
+          ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal]);
     }
     if constexpr (kLane == 0) {
       return v;
