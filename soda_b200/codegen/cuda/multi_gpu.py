@@ -1,4 +1,5 @@
-"""Multi-GPU slab runtime: one process per GPU, halo exchange per pass.
+"""Multi-GPU slab runtime: one process per GPU, halo exchange per group of
+passes.
 
 The grid is split along the outermost (streamed, ``*``) dimension into
 contiguous slabs, one per rank - the dimension the reference itself treats as
@@ -14,6 +15,16 @@ each side that exist in the global grid; at the global border there is no
 ghost, so the kernels' TMA loads zero-fill there exactly as on one GPU.  Every
 stored value therefore has the same dependency cone and the same operation
 order as in the single-GPU run: results are bit-identical.
+
+Exchange groups: temporal blocking one level up.  A rank that holds
+``k x reach`` ghost slices can run ``k`` passes without talking to anybody -
+pass ``j`` of the group also computes the ghost slices the remaining passes
+still need, exactly like a strip of the 2-D kernel recomputes its halo - and
+then swaps ``k x reach`` slices at once.  The redundant work is
+``k x reach / slab`` (0.4 % for the bench: 66 ghost rows per side of a
+16384-row slab, one exchange per 64 iterations instead of eleven), the
+synchronisations with the neighbours drop by ``k``.  ``exchange_every`` picks
+``k`` (default: as many passes as keep the ghost below 2.5 % of the slab).
 
 The reference has no distributed path at all; this file
 is new functionality required by BASELINE.json's north star.
@@ -54,7 +65,8 @@ class SlabRunner:
                rank: Optional[int] = None,
                world: Optional[int] = None,
                group=None,
-               stream_handle: int = 0):
+               stream_handle: int = 0,
+               exchange_every: Optional[int] = None):
     self.program = program
     self.group = group
     self.rank = dist.get_rank(group) if rank is None else rank
@@ -68,10 +80,15 @@ class SlabRunner:
     self.ranges = split_slices(total, self.world)
     self.begin, self.end = self.ranges[self.rank]
     infos = [program.pass_info(i) for i in range(program.num_passes)]
-    self.reach_lo = max(-info.reach_lo[s_dim] for info in infos)
-    self.reach_hi = max(info.reach_hi[s_dim] for info in infos)
     self.pass_reach = [(-info.reach_lo[s_dim], info.reach_hi[s_dim])
                        for info in infos]
+    slab = min(end - begin for begin, end in self.ranges)
+    self.groups = self._make_groups(exchange_every, slab)
+    # ghost depth: what the deepest group needs before its first pass
+    self.reach_lo = max(sum(self.pass_reach[i][0] for i in g)
+                        for g in self.groups)
+    self.reach_hi = max(sum(self.pass_reach[i][1] for i in g)
+                        for g in self.groups)
     for begin, end in self.ranges:
       if end - begin < max(self.reach_lo, self.reach_hi):
         raise ValueError('slab thinner than the halo: use fewer ranks')
@@ -87,6 +104,28 @@ class SlabRunner:
     n = len(program.output_dtypes)
     self.scratch = [[None] * n, [None] * n]
     self.launches = 0
+
+  def _make_groups(self, exchange_every: Optional[int],
+                   slab: int) -> List[List[int]]:
+    """Consecutive passes that run between two halo exchanges."""
+    n = self.program.num_passes
+    if self.world == 1:
+      return [list(range(n))]
+    groups: List[List[int]] = []
+    current: List[int] = []
+    depth = 0
+    budget = max(1, int(slab * 0.025))
+    for index in range(n):
+      reach = max(self.pass_reach[index])
+      full = (len(current) >= exchange_every) if exchange_every else \
+          (depth + reach > budget)
+      if current and full:
+        groups.append(current)
+        current, depth = [], 0
+      current.append(index)
+      depth += reach
+    groups.append(current)
+    return groups
 
   # -- buffers -------------------------------------------------------------------
   def _torch_dtype(self, np_dtype):
@@ -191,57 +230,77 @@ class SlabRunner:
     ghost slices of ``self.inputs`` are refreshed first, so callers only fill
     the slices they own.
 
-    With ``overlap`` every pass but the last is issued as three launches: the
-    slices next to each slab boundary (what the neighbours need for the next
-    pass) first, then the halo exchange of those slices is started, then the
-    interior is computed while the exchange is in flight.
+    Passes run in exchange groups (module docstring).  Inside a group pass ``j``
+    stores its own slices plus the ghost slices the later passes of the group
+    still read; nobody is waited for.  With ``overlap`` the last pass of a group
+    is issued as three launches: the slices next to each slab boundary (what
+    the neighbours need for the next group) first, then the halo exchange of
+    those slices is started, then the interior is computed while the exchange
+    is in flight.
     """
     prog = self.program
     opts = launcher.make_opts(stream=self.stream_handle)
     s_dim = self.dim - 1
+    total = self.global_extent[s_dim]
+    own_lo, own_hi = self.own
     current = self.inputs
-    self.exchange(current, *self.pass_reach[0])
-    for index in range(prog.num_passes):
-      last = index == prog.num_passes - 1
-      if last:
-        target = self.outputs
-      else:
-        bank = self.scratch[index & 1]
-        for o, dt in enumerate(prog.output_dtypes):
-          if bank[o] is None:
-            bank[o] = self._alloc(dt)
-        target = bank
-      box_lo, box_hi = self._boxes(last)
-      if last or self.world == 1:
-        self._launch(index, current, target, box_lo, box_hi, opts)
-        current = target
-        continue
-      next_lo, next_hi = self.pass_reach[index + 1]
-      own_lo, own_hi = self.own
-      # slices of this pass's output that a neighbour needs for the next pass
-      bottom = (own_lo, min(own_hi, own_lo + next_hi)) if self.rank > 0 \
-          else (own_lo, own_lo)
-      top = (max(bottom[1], own_hi - next_lo), own_hi) \
-          if self.rank < self.world - 1 else (own_hi, own_hi)
-      if not overlap:
-        bottom, top = (own_lo, own_lo), (own_hi, own_hi)
 
-      def restricted(lo_slice, hi_slice):
-        lo = [list(b) for b in box_lo]
-        hi = [list(b) for b in box_hi]
-        for o in range(len(lo)):
-          lo[o][s_dim] = max(lo[o][s_dim], lo_slice)
-          hi[o][s_dim] = max(lo[o][s_dim], min(hi[o][s_dim], hi_slice))
-        return lo, hi
+    def depth(group):
+      return (sum(self.pass_reach[i][0] for i in group),
+              sum(self.pass_reach[i][1] for i in group))
 
-      for lo_slice, hi_slice in (bottom, top):
-        if hi_slice > lo_slice:
-          self._launch(index, current, target, *restricted(lo_slice, hi_slice),
+    self.exchange(current, *depth(self.groups[0]))
+    for g, group in enumerate(self.groups):
+      for k, index in enumerate(group):
+        last = index == prog.num_passes - 1
+        if last:
+          target = self.outputs
+        else:
+          bank = self.scratch[index & 1]
+          for o, dt in enumerate(prog.output_dtypes):
+            if bank[o] is None:
+              bank[o] = self._alloc(dt)
+          target = bank
+        box_lo, box_hi = self._boxes(last)
+        # ghost slices the rest of the group still needs from this pass
+        rest_lo = sum(self.pass_reach[i][0] for i in group[k + 1:])
+        rest_hi = sum(self.pass_reach[i][1] for i in group[k + 1:])
+        lo_slice = max(0, own_lo - rest_lo) if self.begin > 0 else own_lo
+        hi_slice = min(self.local_extent[s_dim], own_hi + rest_hi) \
+            if self.end < total else own_hi
+        if not last:
+          for o in range(len(box_lo)):
+            box_lo[o][s_dim] = lo_slice
+            box_hi[o][s_dim] = max(lo_slice, hi_slice)
+        end_of_group = k == len(group) - 1
+        if last or self.world == 1 or not end_of_group:
+          self._launch(index, current, target, box_lo, box_hi, opts)
+          current = target
+          continue
+        next_lo, next_hi = depth(self.groups[g + 1])
+        # slices of this pass's output that a neighbour needs for the next group
+        bottom = (own_lo, min(own_hi, own_lo + next_hi)) if self.rank > 0 \
+            else (own_lo, own_lo)
+        top = (max(bottom[1], own_hi - next_lo), own_hi) \
+            if self.rank < self.world - 1 else (own_hi, own_hi)
+        if not overlap:
+          bottom, top = (own_lo, own_lo), (own_hi, own_hi)
+
+        def restricted(lo_s, hi_s):
+          lo = [list(b) for b in box_lo]
+          hi = [list(b) for b in box_hi]
+          for o in range(len(lo)):
+            lo[o][s_dim] = max(lo[o][s_dim], lo_s)
+            hi[o][s_dim] = max(lo[o][s_dim], min(hi[o][s_dim], hi_s))
+          return lo, hi
+
+        for lo_s, hi_s in (bottom, top):
+          if hi_s > lo_s:
+            self._launch(index, current, target, *restricted(lo_s, hi_s), opts)
+        pending = self.start_exchange(target, next_lo, next_hi)
+        if top[0] > bottom[1]:
+          self._launch(index, current, target, *restricted(bottom[1], top[0]),
                        opts)
-      pending = self.start_exchange(target, next_lo, next_hi)
-      if top[0] > bottom[1]:
-        self._launch(index, current, target, *restricted(bottom[1], top[0]),
-                     opts)
-      for work in pending:
-        work.wait()
-      current = target
+        for work in pending:
+          work.wait()
+        current = target

@@ -157,8 +157,8 @@ def packable(stencil) -> bool:
   only adds, subtracts and multiplies loads, fp32 literals and integer
   literals.  Anything else (division, calls, comparisons, double literals,
   integer tensors) keeps the scalar path.  A pair holds cells ``(u, u + C/2)``
-  of a lane, so dimension-0 offsets cost one shuffle and one move per lane
-  boundary crossed, whatever their parity (soda_stream.cuh)."""
+  of a lane, so a dimension-0 offset costs one shuffle and one move per lane
+  boundary crossed, whatever its parity (soda_stream.cuh)."""
   float_t = ir.Type('float')
   types = stencil.input_types + stencil.output_types + tuple(
       stencil.local_types)
@@ -190,6 +190,17 @@ def packable(stencil) -> bool:
       if let.haoda_type not in (None, float_t) or not ok(let.expr):
         return False
     if not ok(stmt.expr):
+      return False
+    # every load at a dimension-0 offset costs a shuffle and a move per lane
+    # to rotate a pair across the lane boundary; measured on B200, packing
+    # pays while a statement has at most two of them (5/7-point stars: +8 % at
+    # time block 6; the 9-point box of seidel2d with six: -5 %)
+    shifted = {
+        tuple(a - b for a, b in zip(ref.idx, stmt.ref.idx))
+        for ref in _stmt_loads(stmt, stencil.param_names)
+        if ref.idx[0] != stmt.ref.idx[0]
+    }
+    if len(shifted) > 2:
       return False
   return True
 

@@ -22,7 +22,7 @@ def _free_port():
 
 
 def _worker(rank, world, port, name, overrides, time_block, extent, lib, seed,
-            result_dir):
+            result_dir, exchange_every=None, expect_groups=None):
   sys.path.insert(0, common.ROOT)
   os.environ['MASTER_ADDR'] = '127.0.0.1'
   os.environ['MASTER_PORT'] = str(port)
@@ -32,7 +32,9 @@ def _worker(rank, world, port, name, overrides, time_block, extent, lib, seed,
     st = common.stencil(name, **overrides)
     prog = launcher.CudaProgram(lib)
     runner = multi_gpu.SlabRunner(prog, extent, torch.device('cpu'), rank=rank,
-                                  world=world)
+                                  world=world, exchange_every=exchange_every)
+    if expect_groups is not None:
+      assert [len(g) for g in runner.groups] == expect_groups, runner.groups
     inputs = common.make_inputs(st, extent, seed=seed)
     lo, hi = runner.own
     for tensor, iname in zip(runner.inputs, st.input_names):
@@ -50,14 +52,14 @@ def _worker(rank, world, port, name, overrides, time_block, extent, lib, seed,
 
 
 def run_case(tmp_path, name, extent, world, time_block=None, options=None,
-             seed=3, **overrides):
+             seed=3, exchange_every=None, expect_groups=None, **overrides):
   from tests.emu import build_emu
   st = common.stencil(name, **overrides)
   lib = build_emu.build_emu_library(st, time_block=time_block, options=options)
   port = _free_port()
   mp.spawn(_worker,
            args=(world, port, name, overrides, time_block, extent, lib, seed,
-                 str(tmp_path)),
+                 str(tmp_path), exchange_every, expect_groups),
            nprocs=world, join=True)
   inputs = common.make_inputs(st, extent, seed=seed)
   want = common.oracle_outputs(st, inputs)
@@ -93,3 +95,44 @@ def test_multi_input_dag_two_ranks(tmp_path):
 def test_heat3d_two_ranks(tmp_path):
   run_case(tmp_path, 'heat3d', (40, 12, 20), 2, time_block=2, iterate=4,
            options={'rows': 8})
+
+
+@pytest.mark.parametrize('every,groups', [(2, [2, 2, 1]), (5, [5]), (1, [1] * 5)])
+def test_exchange_groups_three_ranks(tmp_path, every, groups):
+  """Several passes between two halo exchanges: every pass of a group also
+  computes the ghost slices the rest of the group still reads; results stay
+  bit-identical to the single-rank oracle."""
+  run_case(tmp_path, 'jacobi2d', (70, 90), 3, time_block=2, iterate=9,
+           exchange_every=every, expect_groups=groups)
+
+
+def test_exchange_groups_one_sided_and_3d(tmp_path):
+  run_case(tmp_path, 'blur', (300, 60), 2, time_block=1, iterate=3,
+           exchange_every=3, expect_groups=[3])
+  run_case(tmp_path, 'heat3d', (40, 12, 30), 2, time_block=1, iterate=4,
+           options={'rows': 8}, exchange_every=2, expect_groups=[2, 2])
+
+
+def test_default_groups_keep_the_ghost_small():
+  from soda_b200.codegen.cuda import multi_gpu
+
+  class FakeInfo:
+    def __init__(self):
+      self.reach_lo = [0, -6, 0]
+      self.reach_hi = [0, 6, 0]
+
+  class FakeProgram:
+    dim = 2
+    num_passes = 11
+    input_dtypes = output_dtypes = []
+    def pass_info(self, index):
+      return FakeInfo()
+
+  runner = multi_gpu.SlabRunner(FakeProgram(), (16384, 8 * 16384),
+                                torch.device('cpu'), rank=3, world=8)
+  # 66 ghost rows per side of a 16384-row slab: one exchange per step
+  assert [len(g) for g in runner.groups] == [11]
+  assert (runner.reach_lo, runner.reach_hi) == (66, 66)
+  thin = multi_gpu.SlabRunner(FakeProgram(), (16384, 8 * 512),
+                              torch.device('cpu'), rank=0, world=8)
+  assert [len(g) for g in thin.groups] == [2, 2, 2, 2, 2, 1]  # 12 of 512 rows

@@ -100,10 +100,10 @@ def test_packed_fp32_eligibility():
   """Packed FADD2/FFMA2 evaluation: fp32 programs that only add, subtract
   and multiply."""
   want = {'jacobi2d': True, 'jacobi3d': True, 'heat3d': True,
-          'seidel2d': True,
+          'seidel2d': False,  # nine loads, six at dimension-0 offsets
           'blur': False, 'sobel2d': False, 'xcorr': False, 'erosion': False,
           'denoise2d': False, 'denoise3d': False,   # sqrt, division
-          'contrast': True}
+          'contrast': False}
   for name, flag in want.items():
     assert plan.packable(common.stencil(name)) == flag, name
   p = plan.make_pass_plan(common.stencil('jacobi2d'), time_block=2)
