@@ -226,7 +226,33 @@ __global__ void __launch_bounds__(kThreads)
   // stream offset of column c0 of the current tile is base + c0
   long long base = (tile + idx0) * g.aligned + in_tile + g.stencil_offset;
   int limit = actual_tile_size(g, 0, idx0) - cut0;  // first column not stored
+  // fast path: all kRun cells of this lane lie in the valid range of one tile
+  {
+    const int c_last = c0 + 32 * (kRun - 1);
+    const bool same_tile = idx0 == last || c_last < g.tile_stride[0] + lo0;
+    if (same_tile && c_last < limit && x + 32 * (kRun - 1) < x_hi) {
+      const long long t0 = base + c0;
+      if (g.banks == 1) {
+        const T* src = static_cast<const T*>(g.bank[0]) + t0;
+        T v[kRun];
 #pragma unroll
+        for (int k = 0; k < kRun; ++k) v[k] = src[32 * k];
+#pragma unroll
+        for (int k = 0; k < kRun; ++k) out[x + 32 * k] = v[k];
+      } else {
+        T v[kRun];
+#pragma unroll
+        for (int k = 0; k < kRun; ++k) {
+          const BankCursor in(g, t0 + 32 * k);
+          v[k] = static_cast<const T*>(g.bank[in.bank])[in.pos];
+        }
+#pragma unroll
+        for (int k = 0; k < kRun; ++k) out[x + 32 * k] = v[k];
+      }
+      return;
+    }
+  }
+#pragma unroll 1
   for (int k = 0; k < kRun; ++k, x += 32, c0 += 32) {
     if (x >= x_hi) return;
     while (c0 >= g.tile_stride[0] + lo0 && idx0 < last) {

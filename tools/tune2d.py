@@ -28,18 +28,16 @@ def variants():
                                                       (6, 12), (3, 4)):
       yield tb, {'warps': warps, 'chunk': chunk, 'stages': stages}
     return
-  for tb in (5, 6, 8):
-    yield tb, {'no_pipeline': True}
-  for tb in (4, 5, 6, 7, 8, 10):
-    for stages in (2, 3):
-      for warps in (2, 4):
-        yield tb, {'cells': 8, 'stages': stages, 'warps': warps,
-                   'no_pipeline': True}
-    yield tb, {'cells': 8, 'stages': 3, 'warps': 4}
-    yield tb, {'cells': 8, 'stages': 3, 'warps': 4, 'no_pipeline': True,
-               'no_pack': True}
-    yield tb, {'cells': 8, 'stages': 3, 'warps': 4, 'no_pipeline': True,
-               'chunk': 3}
+  for tb in (6, 7):
+    for stages in (2, 3, 4):
+      for warps in (2, 4, 8):
+        yield tb, {'stages': stages, 'warps': warps}
+    yield tb, {'chunk': 3}
+    yield tb, {'chunk': 12, 'stages': 2}
+    yield tb, {'min_blocks': 3}
+    yield tb, {'no_pack': True}
+  yield 8, {'cells': 8, 'stages': 2, 'warps': 2}
+  yield 8, {}
 
 
 def stencil():

@@ -23,6 +23,20 @@ ITERATE = 12
 
 def variants():
   out = []
+  if os.environ.get('SODA_TUNE_SET') == 'final':
+    for name in ('jacobi3d', 'heat3d'):
+      for rows, cy in ((16, 4), (24, 4), (32, 4), (16, 2), (32, 2), (12, 4)):
+        for mb in (2, 3, 4):
+          out.append((name, {'iterate': ITERATE}, 2,
+                      {'rows': rows, 'cy': cy, 'min_blocks': mb}))
+      out.append((name, {'iterate': ITERATE}, 2, {'pack': True}))
+      out.append((name, {'iterate': ITERATE}, 2, {}))
+      out.append((name, {'iterate': ITERATE}, 1, {}))
+    for rows, cy in ((16, 1), (12, 1), (24, 1), (16, 2)):
+      for mb in (1, 2):
+        out.append(('denoise3d', {}, 1,
+                    {'rows': rows, 'cy': cy, 'min_blocks': mb}))
+    return out
   if os.environ.get('SODA_TUNE_SET') == 'tb2':
     for name in ('jacobi3d', 'heat3d'):
       for rows, cy in ((16, 2), (32, 2), (32, 4), (16, 4), (24, 4), (48, 4)):
