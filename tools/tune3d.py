@@ -32,8 +32,8 @@ def variants():
       out.append((name, {'iterate': ITERATE}, 2, {'pack': True}))
       out.append((name, {'iterate': ITERATE}, 2, {}))
       out.append((name, {'iterate': ITERATE}, 1, {}))
-    for rows, cy in ((16, 1), (12, 1), (24, 1), (16, 2)):
-      for mb in (1, 2):
+    for rows, cy in ((20, 1), (24, 1), (28, 1), (32, 1)):
+      for mb in (1,):
         out.append(('denoise3d', {}, 1,
                     {'rows': rows, 'cy': cy, 'min_blocks': mb}))
     return out
