@@ -40,16 +40,35 @@ _NP = {
 
 
 def np_dtype(t: ir.Type):
+  """NumPy type that holds a value of ``t`` (for ``uintN`` / ``intN`` that C++
+  does not have: the container the reference's ``ap_uint<N>`` array occupies)."""
   name = str(t)
   if name in _NP:
     return _NP[name]
-  return np.dtype(t.numpy_name).type
+  return np.dtype(t.container.numpy_name).type
+
+
+def _wrap(arr, t: ir.Type):
+  """Keeps the low N bits of an integer array, sign-extended for ``intN``: what
+  assigning to ``ap_uint<N>`` / ``ap_int<N>`` does."""
+  bits = t.width_in_bits
+  wide = np.asarray(arr).astype(np.int64)
+  wide = wide & ((1 << bits) - 1)
+  if t.is_signed:
+    sign = 1 << (bits - 1)
+    wide = (wide ^ sign) - sign
+  return wide.astype(np_dtype(t))
 
 
 def _as(value, t: ir.Type):
   """C++ conversion of ``value`` (array or scalar) to type ``t``."""
   dtype = np_dtype(t)
   arr = np.asarray(value)
+  if t.is_lowerable:
+    if arr.dtype.kind == 'f':
+      with np.errstate(invalid='ignore'):
+        arr = np.trunc(arr).astype(np.int64)
+    return _wrap(arr, t)
   if arr.dtype == dtype:
     return arr
   if arr.dtype.kind == 'f' and np.dtype(dtype).kind in 'iu':
@@ -209,6 +228,8 @@ def run(stencil, inputs: Dict[str, np.ndarray],
       raise TypeError('input %s must be %s' % (name, stmt.haoda_type))
     if tuple(arr.shape[::-1]) != extent:
       raise ValueError('all inputs must share one extent')
+    if stmt.haoda_type.is_lowerable:
+      arr = _wrap(arr, stmt.haoda_type)  # an ap_uint<N> array holds N bits
     data[name] = arr
 
   tensors = stencil.chronological_tensors
@@ -234,6 +255,7 @@ def run(stencil, inputs: Dict[str, np.ndarray],
             slice(box[d][0] + delta[d], box[d][1] + delta[d])
             for d in reversed(range(dim)))
         return data[ref.name][index]
+
 
       variables = {}
       evaluator = _Evaluator(load, variables)

@@ -3,6 +3,7 @@ import hashlib
 import os
 import shutil
 import subprocess
+import threading
 from typing import Dict, List, Optional
 
 from soda_b200.codegen.cuda import emit
@@ -14,6 +15,16 @@ INCLUDE_DIR = os.path.join(os.path.dirname(PACKAGE_DIR), 'include')
 BUILD_DIR = os.path.join(PACKAGE_DIR, '_build')
 
 ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
+
+# two threads asking for the same library (identical generated source) must not
+# write its .cu / run nvcc on it at the same time
+_LOCKS_GUARD = threading.Lock()
+_LOCKS: Dict[str, threading.Lock] = {}
+
+
+def _lock_for(path: str) -> threading.Lock:
+  with _LOCKS_GUARD:
+    return _LOCKS.setdefault(path, threading.Lock())
 
 
 def nvcc_path() -> str:
@@ -72,21 +83,27 @@ def build_library(stencil,
   os.makedirs(BUILD_DIR, exist_ok=True)
   lib = output or library_path(stencil, source, strict_fp)
   src_path = keep_source or (os.path.splitext(lib)[0] + '.cu')
-  if output is None and os.path.exists(lib):
-    return lib
-  with open(src_path, 'w') as fp:
-    fp.write(source)
-  tmp = '%s.%d.tmp' % (lib, os.getpid())
-  cmd = [nvcc_path()] + nvcc_flags(strict_fp) + ['-o', tmp, src_path]
-  if verbose:
-    cmd.insert(1, '-Xptxas')
-    cmd.insert(2, '-v')
-  result = subprocess.run(cmd, capture_output=True, text=True)
-  if result.returncode != 0:
-    raise RuntimeError('nvcc failed:\n%s\n%s' % (' '.join(cmd), result.stderr))
-  if verbose:
-    print(result.stderr)
-  os.replace(tmp, lib)
+  with _lock_for(lib):
+    if output is None and os.path.exists(lib):
+      return lib
+    # other processes (ranks of one job) may build the same library: the source
+    # appears atomically, so nobody compiles a half-written file
+    src_tmp = '%s.%d.%d.tmp' % (src_path, os.getpid(), threading.get_ident())
+    with open(src_tmp, 'w') as fp:
+      fp.write(source)
+    os.replace(src_tmp, src_path)
+    tmp = '%s.%d.%d.tmp' % (lib, os.getpid(), threading.get_ident())
+    cmd = [nvcc_path()] + nvcc_flags(strict_fp) + ['-o', tmp, src_path]
+    if verbose:
+      cmd.insert(1, '-Xptxas')
+      cmd.insert(2, '-v')
+    result = subprocess.run(cmd, capture_output=True, text=True)
+    if result.returncode != 0:
+      raise RuntimeError('nvcc failed:\n%s\n%s' %
+                         (' '.join(cmd), result.stderr))
+    if verbose:
+      print(result.stderr)
+    os.replace(tmp, lib)
   return lib
 
 

@@ -21,6 +21,7 @@ from typing import Dict, List, Optional, Sequence
 
 from soda_b200 import ir, util
 from soda_b200.codegen.cuda import plan as planner
+from soda_b200.optimization import widths
 
 DTYPE_CODES = {
     'uint8': 'SODA_CUDA_U8',
@@ -294,6 +295,8 @@ def emit_program(stencil,
                  options: Optional[Dict] = None) -> str:
   """Returns the text of the generated .cu file for ``stencil``."""
   options = dict(options or {})
+  # integer widths C++ does not have become containers + explicit wraps
+  stencil = widths.lower(stencil)
   dim = stencil.dim
   time_block = planner.choose_time_block(stencil, time_block)
   schedule = planner.pass_schedule(stencil.iterate, time_block)

@@ -240,8 +240,10 @@ def make_pass_plan(stencil,
   for t in stencil.input_types + stencil.output_types + tuple(
       stencil.local_types):
     if not t.is_executable:
-      raise util.SemanticError('type %s is not supported by the CUDA backend' %
-                               t)
+      raise util.SemanticError(
+          'type %s is not supported by the CUDA backend%s' %
+          (t, ' as such: lower it with soda_b200.optimization.widths.lower '
+           '(emit_program does)' if t.is_lowerable else ''))
   if pipelined is None:
     pipelined = dim == 2
   if pipelined and dim != 2:

@@ -103,6 +103,25 @@ class Type:
                 int(m.group(2)) in _STD_INT_WIDTHS)
 
   @property
+  def is_lowerable(self) -> bool:
+    """An integer of 1..31 bits that C++ does not have: stored in the next
+    <cstdint> container and wrapped to its width on every store
+    (soda_b200/optimization/widths.py)."""
+    m = _TYPE_RE.match(self._name)
+    return bool(m and m.group(1) != 'float' and m.group(3) is None and
+                int(m.group(2)) not in _STD_INT_WIDTHS and
+                1 <= int(m.group(2)) <= 31)
+
+  @property
+  def container(self) -> 'Type':
+    """The <cstdint> type that stores a value of this type."""
+    if not self.is_lowerable:
+      return self
+    bits = self.width_in_bits
+    width = 8 if bits <= 8 else 16 if bits <= 16 else 32
+    return Type('%s%d' % ('int' if self.is_signed else 'uint', width))
+
+  @property
   def c_type(self) -> str:
     if self._name in ('float', 'double', 'bool'):
       return self._name

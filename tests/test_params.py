@@ -101,3 +101,71 @@ def test_param_programs_on_gpu(name, extent, kwargs):
   assert prog.launch_count() > before
   with pytest.raises(ValueError):
     prog.run_host(common.make_inputs(st, extent))  # params missing
+
+
+# ---- integer widths C++ does not have (second half) ----
+
+def test_narrow_widths_are_lowered_to_containers_and_wraps():
+  from soda_b200.optimization import widths
+  st = stencil('narrow2d')
+  assert widths.has_narrow_types(st)
+  low = widths.lower(st)
+  assert not widths.has_narrow_types(low)
+  assert [str(t) for t in low.input_types + low.output_types] == ['uint8',
+                                                                  'uint8']
+  text = str(low)
+  assert '& 63' in text and '^ 16) - 16' in text and '& 1023' in text
+  # programs without such types pass through untouched
+  plain = common.stencil('blur')
+  assert widths.lower(plain) is plain
+  # 40-bit integers and custom floats stay unsupported
+  with pytest.raises(util.SemanticError):
+    emit.emit_program(sodac.compile_source(
+        open(os.path.join(EXTRA, 'narrow2d.soda')).read().replace(
+            'uint10', 'uint40')))
+
+
+def _narrow_inputs(st, extent, seed=9):
+  rng = np.random.default_rng(seed)
+  # container bytes with garbage above bit 5: an ap_uint<6> array cannot hold it
+  return {'a': rng.integers(0, 256, extent[::-1]).astype(np.uint8)}
+
+
+def test_narrow_widths_oracles_and_lowering_agree():
+  from soda_b200.optimization import widths
+  st = stencil('narrow2d')
+  extent = (70, 19)
+  inputs = _narrow_inputs(st, extent)
+  a = golden.run(st, inputs)
+  b = emit_cpp.Oracle(st).run(inputs)
+  c = golden.run(widths.lower(st), inputs)  # the rewritten program
+  index = common.box_index(st.valid_box('b', extent))
+  assert np.array_equal(a['b'][index], b['b'][index])
+  assert np.array_equal(a['b'][index], c['b'][index])
+  assert a['b'][index].max() <= 63 and len(np.unique(a['b'][index])) > 20
+
+
+def test_narrow_widths_under_emulation():
+  st = stencil('narrow2d')
+  extent = (90, 21)
+  prog = launcher.CudaProgram(build_emu.build_emu_library(st))
+  assert [str(d) for d in prog.input_dtypes + prog.output_dtypes] == ['uint8',
+                                                                      'uint8']
+  inputs = _narrow_inputs(st, extent)
+  outputs = {'b': np.full(extent[::-1], 77, dtype=np.uint8)}
+  prog.run_host(inputs, outputs)
+  common.assert_matches_oracle(st, extent, outputs,
+                               emit_cpp.Oracle(st).run(inputs), sentinel=77)
+
+
+@pytest.mark.gpu
+def test_narrow_widths_on_gpu():
+  from soda_b200.codegen import cuda as cuda_backend
+  st = stencil('narrow2d')
+  extent = (1000, 211)
+  prog = cuda_backend.compile_stencil(st, time_block=2)
+  inputs = _narrow_inputs(st, extent)
+  outputs = {'b': np.full(extent[::-1], 77, dtype=np.uint8)}
+  prog.run_host(inputs, outputs)
+  common.assert_matches_oracle(st, extent, outputs,
+                               emit_cpp.Oracle(st).run(inputs), sentinel=77)
