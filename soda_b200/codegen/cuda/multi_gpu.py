@@ -146,11 +146,13 @@ class SlabRunner:
 
   # -- halo exchange ----------------------------------------------------------------
   def _comm_view(self, tensor: torch.Tensor) -> torch.Tensor:
-    """NCCL has no unsigned 16/32/64-bit types: exchange the same bits as a
-    signed type."""
-    alias = {torch.uint16: torch.int16, torch.uint32: torch.int32,
-             torch.uint64: torch.int64}
-    return tensor.view(alias[tensor.dtype]) if tensor.dtype in alias else tensor
+    """NCCL (through torch) moves 8-bit, 32/64-bit signed integer and float
+    types only - no int16, no unsigned 16/32/64 (found on B200 with the uint16
+    blur: "Input tensor data type is not supported for NCCL process group:
+    Short").  Halo slices of any other type travel as the same bytes."""
+    native = (torch.int8, torch.uint8, torch.int32, torch.int64, torch.float16,
+              torch.bfloat16, torch.float32, torch.float64)
+    return tensor if tensor.dtype in native else tensor.view(torch.uint8)
 
   def start_exchange(self, tensors: Sequence[torch.Tensor], reach_lo: int,
                      reach_hi: int):

@@ -20,7 +20,9 @@
 
 namespace {
 
-constexpr int kRun = 8;        // consecutive elements per thread
+// consecutive elements per thread: 32 bytes' worth, at least 8
+template <typename T>
+constexpr int kRunOf = sizeof(T) >= 4 ? 8 : 32 / static_cast<int>(sizeof(T)) > 16 ? 16 : 32 / static_cast<int>(sizeof(T));
 constexpr int kThreads = 256;
 
 thread_local std::string g_error;
@@ -120,6 +122,7 @@ struct BankCursor {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
     pack_kernel(const Geometry g, const T* __restrict__ dense) {
+  constexpr int kRun = kRunOf<T>;
   const long long total = g.bank_elems * g.banks;
   long long t = (static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x) * kRun;
   if (t >= total) return;
@@ -180,6 +183,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
     unpack_kernel(const Geometry g, T* __restrict__ dense, int x_lo, int x_hi,
                   int y_lo, int y_hi, int z_lo, int z_hi) {
+  constexpr int kRun = kRunOf<T>;
   // a warp walks 32 * kRun consecutive cells of one row of the valid box, lane
   // l taking cells l, l + 32, ...: loads and stores of a warp are contiguous
   constexpr int kSpan = 32 * kRun;
@@ -337,6 +341,7 @@ int make_geometry(const soda_stream_layout* l, Geometry* g) {
 
 template <typename T>
 int launch_pack(const Geometry& g, const void* dense, cudaStream_t stream) {
+  constexpr int kRun = kRunOf<T>;
   const long long total = g.bank_elems * g.banks;
   const long long threads = (total + kRun - 1) / kRun;
   const long long blocks = (threads + kThreads - 1) / kThreads;
@@ -351,6 +356,7 @@ int launch_pack(const Geometry& g, const void* dense, cudaStream_t stream) {
 
 template <typename T>
 int launch_unpack(const Geometry& g, void* dense, cudaStream_t stream) {
+  constexpr int kRun = kRunOf<T>;
   // valid box of the whole grid (host.py:357-376 over all tiles)
   int lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
   for (int d = 0; d < g.dim; ++d) {
