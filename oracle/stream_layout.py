@@ -21,6 +21,13 @@ kernel with a 3x3 window starts at column 98 = 100 - 3 + 1) all use
 after the first would be fed columns shifted by ``tile_index``; we follow the
 documented layout (+1), which coincides with the literal code for single-tile
 grids (the only case the reference's own tests run).
+
+A quirk kept as is: the un-tiler takes its loop bounds from the window of the
+*first* input (src/soda/codegen/frt/host.py:352-356).  For a program whose first
+input has a smaller window than another one (denoise: ``f`` is read at one
+point, ``u`` in a 5x5 window) every tile after the first therefore also writes
+its leading columns, computed from cells outside the tile
+(tests/test_stream_kernel.py::test_multi_input_seam_quirk).
 """
 import dataclasses
 from typing import List, Sequence, Tuple
