@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU session: 2-D tuning sweep, then ncu captures of the 3-D kernels.
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 python -m pytest tests -m gpu -x -q > $O/pytest_gpu3.log 2>&1; tail -3 $O/pytest_gpu3.log
 python tools/tune2d.py run > $O/tune2d_v3.log 2>&1

@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU session: parity tests, 3-D tuning sweep, ncu of the 2-D time-block-8 kernel
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 python -m pytest tests -m gpu -x -q > $O/pytest_gpu4.log 2>&1; tail -3 $O/pytest_gpu4.log
 python tools/tune3d.py run > $O/tune3d_v1.log 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 python tools/tune2d.py run > $O/tune2d_v4.log 2>&1
 SODA_TUNE_SET=tb2 python tools/tune3d.py run > $O/tune3d_v2.log 2>&1

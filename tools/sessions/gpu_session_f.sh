@@ -1,6 +1,6 @@
 #!/bin/bash
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 export SODA_CUDA_VERBOSE=1
 python -m pytest tests -m gpu -x -q > $O/pytest_gpu7.log 2>&1; tail -3 $O/pytest_gpu7.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 python -m pytest tests -m gpu -x -q > $O/pytest_gpu8.log 2>&1; tail -15 $O/pytest_gpu8.log
 python tools/bench_layout.py > $O/layout_bench.log 2>&1; cat $O/layout_bench.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 python -m pytest tests -m gpu -x -q > $O/pytest_gpu12.log 2>&1; tail -5 $O/pytest_gpu12.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke2.log 2>&1; tail -2 $O/smoke2.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # one 8-GPU box: the bench at N = 1, 2, 4, 8 (what the driver does at round end)
 set -x
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $O/scale_n1.json 2> $O/scale_n1.err
 for N in 2 4 8; do
