@@ -40,11 +40,22 @@ def add_arguments(parser) -> None:
                       'to 4 in 2-D, 2 in 3-D)')
   parser.add_argument('--cuda-cells', type=int, dest='cuda_cells', metavar='N',
                       help='cells per lane in dimension 0 (default: 16 bytes '
-                      'worth)')
+                      'worth, 32 for light 2-D fp32 programs)')
   parser.add_argument('--cuda-rows', type=int, dest='cuda_rows', metavar='N',
-                      help='3-D tile height = warps per CTA (default 8)')
+                      help='3-D tile height (default: 4-6 x the dimension-1 '
+                      'halo, at least 8)')
+  parser.add_argument('--cuda-patch-rows', type=int, dest='cuda_patch_rows',
+                      metavar='N',
+                      help='3-D tile rows owned by one thread (default: 4, 2 '
+                      'or 1 by register budget)')
   parser.add_argument('--cuda-warps', type=int, dest='cuda_warps', metavar='N',
-                      help='2-D strips (warps) per CTA (default 4)')
+                      help='2-D strips (warps) per CTA (default 2 or 4)')
+  parser.add_argument('--cuda-min-blocks', type=int, dest='cuda_min_blocks',
+                      metavar='N', help='CTAs per SM to ask the compiler for')
+  parser.add_argument('--cuda-no-pipeline', action='store_true',
+                      dest='cuda_no_pipeline',
+                      help='2-D: evaluate producers before consumers within a '
+                      'step instead of the pipelined DAG schedule')
   parser.add_argument('--cuda-chunk', type=int, dest='cuda_chunk', metavar='N',
                       help='2-D rows per TMA box')
   parser.add_argument('--cuda-stages', type=int, dest='cuda_stages',
@@ -67,6 +78,9 @@ def options_from_args(args: Optional[argparse.Namespace]) -> Dict:
       'warps': get('cuda_warps'),
       'chunk': get('cuda_chunk'),
       'stages': get('cuda_stages'),
+      'cy': get('cuda_patch_rows'),
+      'min_blocks': get('cuda_min_blocks'),
+      'no_pipeline': bool(get('cuda_no_pipeline')),
       'fast_fp': bool(get('cuda_fast_fp')),
       'no_pack': bool(get('cuda_no_pack')),
   }
