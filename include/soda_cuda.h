@@ -72,7 +72,13 @@ typedef struct soda_cuda_opts {
   int32_t struct_size;
   int32_t device;        /* CUDA device ordinal; -1 = current device */
   void* stream;          /* cudaStream_t; NULL = the default stream */
-  int32_t segment;       /* output slices per CTA along the streamed dimension; 0 = auto */
+  int32_t segment;       /* output slices per CTA along the streamed dimension; 0 = auto:
+                          * the first launch of a pass on a large grid (>= 2^24 cells)
+                          * times a few candidate lengths with CUDA events on `stream`
+                          * and synchronises on them once (the pass is idempotent); later
+                          * launches of the same shape reuse the winner.  Set a length, or
+                          * SODA_CUDA_AUTOTUNE=0 in the environment, when that one-time
+                          * synchronisation is unwanted (e.g. while capturing a CUDA graph) */
   int32_t reserved[5];   /* reserved[0]: chunks of the pipelined host path (copy/compute
                           * overlap of soda_cuda_plan_run_host); 0 = auto, 1 = off */
 } soda_cuda_opts;
