@@ -394,6 +394,10 @@ def make_pass_plan(stencil,
   # dimension 0: strip origins must be multiples of the lane vector (aligned
   # vector stores) and of 16 bytes of every input (TMA faults on a box whose
   # first element is not 16-byte aligned in global memory)
+  # (whole lanes are stored or not: halos and valid widths are multiples of
+  # the lane width; 6-cell lanes, which would cover a 512-wide grid with three
+  # strips instead of five, fail on exactly this: lcm(6 cells, 16 bytes) = 12
+  # cells of low halo eat the gain)
   align0 = max([cells] + [
       128 // t.width_in_bits for t in stencil.input_types
   ])
