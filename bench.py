@@ -84,7 +84,7 @@ class ClockSampler:
     try:
       self.proc = subprocess.Popen([
           'nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
-          '--format=csv,noheader,nounits', '-lms', '100'
+          '--format=csv,noheader,nounits', '-lms', '20'
       ], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except OSError:
       return
