@@ -64,7 +64,8 @@ typedef enum soda_cuda_status {
 typedef enum soda_cuda_dtype {
   SODA_CUDA_U8 = 0, SODA_CUDA_I8 = 1, SODA_CUDA_U16 = 2, SODA_CUDA_I16 = 3,
   SODA_CUDA_U32 = 4, SODA_CUDA_I32 = 5, SODA_CUDA_U64 = 6, SODA_CUDA_I64 = 7,
-  SODA_CUDA_F32 = 8, SODA_CUDA_F64 = 9
+  SODA_CUDA_F32 = 8, SODA_CUDA_F64 = 9,
+  SODA_CUDA_F16 = 10 /* IEEE binary16, the DSL's `half` */
 } soda_cuda_dtype;
 
 /* Run-time options; zero-initialise and set struct_size = sizeof(soda_cuda_opts). */

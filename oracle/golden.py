@@ -35,6 +35,8 @@ from soda_b200 import ir
 _NP = {
     'float': np.float32,
     'double': np.float64,
+    # IEEE binary16: NumPy rounds every float16 operation once, to nearest-even
+    'half': np.float16,
     'bool': np.bool_,
 }
 

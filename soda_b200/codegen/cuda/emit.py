@@ -32,6 +32,7 @@ DTYPE_CODES = {
     'int32': 'SODA_CUDA_I32',
     'uint64': 'SODA_CUDA_U64',
     'int64': 'SODA_CUDA_I64',
+    'half': 'SODA_CUDA_F16',
     'float': 'SODA_CUDA_F32',
     'double': 'SODA_CUDA_F64',
 }

@@ -18,7 +18,7 @@ MAX_DIM = 3
 MAX_TENSORS = 8
 
 DTYPES = ('uint8', 'int8', 'uint16', 'int16', 'uint32', 'int32', 'uint64',
-          'int64', 'float32', 'float64')
+          'int64', 'float32', 'float64', 'float16')
 
 EXPORTED_SYMBOLS = (
     'soda_cuda_info',

@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <type_traits>
+
 // `param` arrays of a program (generated code) live in constant memory
 #define SODA_CONSTANT __constant__
 
@@ -145,6 +147,16 @@ __device__ __forceinline__ T shfl_rel(T v) {
     bits = kDelta > 0 ? shfl_bits_down(bits, kDelta) : shfl_bits_up(bits, -kDelta);
     T r;
     memcpy(&r, &bits, 4);
+    return r;
+  } else if constexpr (!std::is_integral<T>::value) {
+    // 16-bit floating cells (soda::half_t): the bit pattern travels
+    unsigned short raw;
+    memcpy(&raw, &v, sizeof(T));
+    unsigned bits = raw;
+    bits = kDelta > 0 ? shfl_bits_down(bits, kDelta) : shfl_bits_up(bits, -kDelta);
+    raw = static_cast<unsigned short>(bits);
+    T r;
+    memcpy(&r, &raw, sizeof(T));
     return r;
   } else {
     // 8- and 16-bit cells travel sign- or zero-extended in a 32-bit register;

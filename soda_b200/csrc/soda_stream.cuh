@@ -35,6 +35,7 @@
 #else
 #include "soda_ptx.cuh"
 #endif
+#include "soda_half.cuh"
 
 namespace soda {
 

@@ -34,8 +34,9 @@ class Type:
   """A SODA element type such as ``uint16``, ``int32``, ``float``, ``double``.
 
   Arbitrary widths (``uint6``, ``int27``, ``float18_3``) parse and print, but
-  only the widths C++ has (<cstdint> integers, float, double) can be executed
-  by the CUDA backend and the oracle; ``c_type`` raises for the others.
+  only the widths C++ has (<cstdint> integers, float, double) and IEEE ``half``
+  can be executed by the CUDA backend and the oracle; ``c_type`` raises for
+  the others.
   """
   __slots__ = ('_name',)
 
@@ -96,7 +97,7 @@ class Type:
   @property
   def is_executable(self) -> bool:
     """Whether C++ has this exact type (so oracle and GPU agree bit for bit)."""
-    if self._name in ('float', 'double', 'bool'):
+    if self._name in ('float', 'double', 'half', 'bool'):
       return True
     m = _TYPE_RE.match(self._name)
     return bool(m and m.group(1) != 'float' and m.group(3) is None and
@@ -125,10 +126,12 @@ class Type:
   def c_type(self) -> str:
     if self._name in ('float', 'double', 'bool'):
       return self._name
+    if self._name == 'half':
+      return 'soda::half_t'  # soda_b200/csrc/soda_half.cuh
     if not self.is_executable:
       raise util.SemanticError(
           'type %s has no C++ equivalent; the CUDA backend and the oracle '
-          'support uint8/16/32/64, int8/16/32/64, float and double' %
+          'support uint8/16/32/64, int8/16/32/64, half, float and double' %
           self._name)
     return self._name + '_t'
 
@@ -138,6 +141,8 @@ class Type:
       return 'float32'
     if self._name == 'double':
       return 'float64'
+    if self._name == 'half':
+      return 'float16'
     if self._name == 'bool':
       return 'bool'
     if not self.is_executable:
@@ -157,6 +162,7 @@ INT64 = Type('int64')
 UINT64 = Type('uint64')
 FLOAT = Type('float')
 DOUBLE = Type('double')
+HALF = Type('half')
 
 
 def _promote(t: Type) -> Type:
@@ -170,7 +176,8 @@ def _promote(t: Type) -> Type:
 
 def common_type(a: Type, b: Type) -> Type:
   """C++ usual arithmetic conversions for two executable types."""
-  for t in (DOUBLE, FLOAT):
+  # half ranks below float and above every integer type, like _Float16
+  for t in (DOUBLE, FLOAT, HALF):
     if a == t or b == t:
       return t
   a, b = _promote(a), _promote(b)

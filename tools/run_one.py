@@ -36,7 +36,10 @@ def main():
     overrides['iterate'] = args.iterate
   if args.cr:
     overrides['computation_reuse'] = args.cr
-  with open(os.path.join(ROOT, 'tests', 'src', args.program + '.soda')) as fp:
+  path = os.path.join(ROOT, 'tests', 'src', args.program + '.soda')
+  if not os.path.exists(path):  # programs of our own (params, widths, half)
+    path = os.path.join(ROOT, 'tests', 'src_extra', args.program + '.soda')
+  with open(path) as fp:
     st = sodac.compile_source(fp.read(), **overrides)
   options = json.loads(args.options)
   lib = cuda_build.build_library(st, args.tb, options)
