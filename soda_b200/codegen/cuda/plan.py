@@ -152,18 +152,26 @@ def default_cells(stencil) -> int:
 
 
 def packable(stencil) -> bool:
-  """Whether the program can be evaluated two cells at a time with packed fp32
-  instructions (FADD2 / FFMA2): every tensor is ``float`` and every statement
-  only adds, subtracts and multiplies loads, fp32 literals and integer
-  literals.  Anything else (division, calls, comparisons, double literals,
-  integer tensors) keeps the scalar path.  A pair holds cells ``(u, u + C/2)``
-  of a lane, so a dimension-0 offset costs one shuffle and one move per lane
-  boundary crossed, whatever its parity (soda_stream.cuh)."""
-  float_t = ir.Type('float')
+  """Whether the program can be evaluated two cells at a time with packed
+  instructions (fp32: FADD2 / FFMA2, half: HADD2 / HMUL2): every tensor has the
+  same type, ``float`` or ``half``, and every statement only adds, subtracts
+  and multiplies loads, literals of that type (for half: a ``half(...)`` cast
+  of a literal) and integer literals.  Anything else (division, calls,
+  comparisons, wider literals - a float literal makes a half operation a float
+  one -, integer tensors) keeps the scalar path.  A pair holds cells
+  ``(u, u + C/2)`` of a lane, so a dimension-0 offset costs one shuffle and one
+  move per lane boundary crossed, whatever its parity (soda_stream.cuh)."""
   types = stencil.input_types + stencil.output_types + tuple(
       stencil.local_types)
-  if any(t != float_t for t in types):
+  elem_t = types[0]
+  if elem_t not in (ir.FLOAT, ir.HALF) or any(t != elem_t for t in types):
     return False
+
+  def literal(node) -> bool:
+    while isinstance(node, ir.Operand) or (isinstance(node, ir.BinaryOp) and
+                                           node.singleton):
+      node = node.inner if isinstance(node, ir.Operand) else node.operand[0]
+    return isinstance(node, ir.Num)
 
   def ok(node) -> bool:
     if isinstance(node, ir.Operand):
@@ -171,9 +179,11 @@ def packable(stencil) -> bool:
     if isinstance(node, (ir.Ref, ir.Var)):
       return True
     if isinstance(node, ir.Num):
-      return node.literal_type in (float_t, ir.INT32)
+      return node.literal_type in (elem_t, ir.INT32)
     if isinstance(node, ir.Cast):
-      return node.haoda_type == float_t and ok(node.expr)
+      # a cast of a literal is a scalar of the element type, broadcast
+      return node.haoda_type == elem_t and (literal(node.expr) or
+                                            ok(node.expr))
     if isinstance(node, ir.Unary):
       return all(op in '+-' for op in node.operator) and ok(node.operand)
     if isinstance(node, ir.AddSub):
@@ -185,6 +195,7 @@ def packable(stencil) -> bool:
       return ok(node.operand[0])
     return False
 
+  float_t = elem_t
   for stmt in list(stencil.local_stmts) + list(stencil.output_stmts):
     for let in stmt.let:
       if let.haoda_type not in (None, float_t) or not ok(let.expr):
@@ -451,7 +462,8 @@ def make_tuned_pass_plan(stencil, time_block: int,
 
   * 2-D: 8 fp32 cells per lane instead of 4 (half the strip overlap and half
     the shuffles per cell) while the register windows stay below ~160
-    registers; pipelined schedule.
+    registers; pipelined schedule.  (16-bit cells stay at 8 per lane: a warp's
+    strip is one TMA box, at most 256 elements wide.)
   * 3-D: unpacked arithmetic; as many patch rows per thread (4, 2, 1) as keep
     the windows below ~120 registers; tile rows = 4 x the dimension-1 halo,
     at least 8 - small CTAs, several per SM, hide the per-step barrier better

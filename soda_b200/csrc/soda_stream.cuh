@@ -101,6 +101,9 @@ __device__ __forceinline__ auto cast_to(From v) {
   if constexpr (std::is_same<From, F2>::value) {
     static_assert(std::is_same<To, float>::value, "packed values are fp32");
     return v;
+  } else if constexpr (std::is_same<From, H2>::value) {
+    static_assert(std::is_same<To, half_t>::value, "packed values are half");
+    return v;
   } else {
     return To(v);
   }
@@ -117,10 +120,32 @@ using CarrierOf = typename std::conditional<
     typename std::conditional<std::is_signed<T>::value, int, unsigned>::type,
     T>::type;
 
+// The pair type of a packed program's cells: fp32 pairs (F2, one 64-bit
+// register pair, FADD2 / FFMA2) or binary16 pairs (H2, one 32-bit register,
+// HADD2 / HMUL2).
+template <typename T> struct PairOf { using type = T; };
+template <> struct PairOf<float> { using type = F2; };
+template <> struct PairOf<half_t> { using type = H2; };
+__device__ __forceinline__ F2 pair_pack(float lo, float hi) { return f2_pack(lo, hi); }
+__device__ __forceinline__ H2 pair_pack(half_t lo, half_t hi) { return h2_pack(lo, hi); }
+// a pair that is a value in its own right (see f2_pack_once); a binary16 pair
+// is one register anyway
+__device__ __forceinline__ F2 pair_pack_once(float lo, float hi) { return f2_pack_once(lo, hi); }
+__device__ __forceinline__ H2 pair_pack_once(half_t lo, half_t hi) { return h2_pack(lo, hi); }
+__device__ __forceinline__ float pair_lo(F2 v) { return f2_lo(v); }
+__device__ __forceinline__ float pair_hi(F2 v) { return f2_hi(v); }
+__device__ __forceinline__ half_t pair_lo(H2 v) { return h2_lo(v); }
+__device__ __forceinline__ half_t pair_hi(H2 v) { return h2_hi(v); }
+template <int kDelta>
+__device__ __forceinline__ F2 pair_shfl(F2 v) { return f2_shfl<kDelta>(v); }
+template <int kDelta>
+__device__ __forceinline__ H2 pair_shfl(H2 v) { return shfl_rel<kDelta>(v); }
+
 // A lane owns kCells cells = kUnits units of kPack cells.
 template <class Prog, int N>
 using UnitOf = typename std::conditional<
-    Prog::kPack == 2, F2, CarrierOf<typename Prog::template T<N>>>::type;
+    Prog::kPack == 2, typename PairOf<typename Prog::template T<N>>::type,
+    CarrierOf<typename Prog::template T<N>>>::type;
 template <class Prog>
 constexpr int kUnitsOf = Prog::kCells / Prog::kPack;
 
@@ -131,7 +156,7 @@ __device__ __forceinline__ void units_from_cells(
 #pragma unroll
   for (int u = 0; u < kUnitsOf<Prog>; ++u) {
     if constexpr (Prog::kPack == 2) {
-      units[u] = f2_pack_once(cells[u], cells[u + kUnitsOf<Prog>]);
+      units[u] = pair_pack_once(cells[u], cells[u + kUnitsOf<Prog>]);
     } else {
       units[u] = cells[u];
     }
@@ -145,8 +170,8 @@ __device__ __forceinline__ void cells_from_units(
 #pragma unroll
   for (int u = 0; u < kUnitsOf<Prog>; ++u) {
     if constexpr (Prog::kPack == 2) {
-      cells[u] = f2_lo(units[u]);
-      cells[u + kUnitsOf<Prog>] = f2_hi(units[u]);
+      cells[u] = pair_lo(units[u]);
+      cells[u + kUnitsOf<Prog>] = pair_hi(units[u]);
     } else {
       cells[u] = static_cast<typename Prog::template T<N>>(units[u]);
     }
@@ -185,7 +210,7 @@ __device__ __forceinline__ void clear_rings(Rings<Prog>& rings) {
 #pragma unroll
         for (int u = 0; u < kUnitsOf<Prog>; ++u) {
           if constexpr (Prog::kPack == 2) {
-            r[s][j][u] = f2_splat(0.0f);
+            r[s][j][u] = pair_pack(T(0), T(0));
           } else {
             r[s][j][u] = T(0);
           }
@@ -265,8 +290,8 @@ struct Access {
     typename Prog::template T<P> v;
     if constexpr (Prog::kPack == 2) {
       constexpr int kH = kUnitsOf<Prog>;
-      const F2 unit = ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal % kH];
-      v = kLocal >= kH ? f2_hi(unit) : f2_lo(unit);
+      const auto unit = ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal % kH];
+      v = kLocal >= kH ? pair_hi(unit) : pair_lo(unit);
     } else {
       v = static_cast<typename Prog::template T<P>>(
           ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal]);
@@ -304,21 +329,21 @@ struct Access {
         constexpr int kLocal = kFirst - kLane * Prog::kCells;
         if constexpr (kLocal < kHalf) {
           // a whole unit of this or a neighbouring lane
-          const F2 v = ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal];
+          const auto v = ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal];
           if constexpr (kLane == 0) {
             return v;
           } else {
-            return f2_shfl<kLane>(v);
+            return pair_shfl<kLane>(v);
           }
         } else {
           // rotated across a lane boundary: (hi of unit j in lane kLane,
           // lo of unit j in lane kLane + 1)
-          const F2 v = ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal - kHalf];
-          float first = f2_hi(v);
-          float second = f2_lo(v);
+          const auto v = ring_of<P, Prog>(ctx.rings)[kSlot][kRow][kLocal - kHalf];
+          auto first = pair_hi(v);
+          auto second = pair_lo(v);
           if constexpr (kLane != 0) first = shfl_rel<kLane>(first);
           if constexpr (kLane + 1 != 0) second = shfl_rel<kLane + 1>(second);
-          return f2_pack(first, second);
+          return pair_pack(first, second);
         }
       }
     } else {
@@ -783,10 +808,10 @@ struct Step3D {
 
   // packed: cells (kCol, kCol + kCells / 2)
   template <int P, int kDistance, int kCol, int kRow>
-  __device__ __forceinline__ F2 plane_unit() const {
+  __device__ __forceinline__ auto plane_unit() const {
     constexpr int kHalf = kUnitsOf<Prog>;
-    return f2_pack(plane_cell<P, kDistance, kCol, kRow>(),
-                   plane_cell<P, kDistance, kCol + kHalf, kRow>());
+    return pair_pack(plane_cell<P, kDistance, kCol, kRow>(),
+                     plane_cell<P, kDistance, kCol + kHalf, kRow>());
   }
 };
 
@@ -873,8 +898,8 @@ __device__ __forceinline__ void export_rows_3d(Step& st) {
         const auto& units = newest_units<N, J, Prog>(st);
 #pragma unroll
         for (int u = 0; u < kUnitsOf<Prog>; ++u) {
-          tmp.v[2 * u] = f2_lo(units[u]);
-          tmp.v[2 * u + 1] = f2_hi(units[u]);
+          tmp.v[2 * u] = pair_lo(units[u]);
+          tmp.v[2 * u + 1] = pair_hi(units[u]);
         }
       } else {
         T cells[kC];

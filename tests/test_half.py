@@ -27,7 +27,16 @@ from tests.emu import build_emu
 EXTRA = os.path.join(common.ROOT, 'tests', 'src_extra')
 CASES = [('smooth2d_half', (150, 37), {}),
          ('smooth2d_half', (97, 40), {'time_block': 2}),
-         ('mix3d_half', (40, 21, 13), {})]
+         ('mix3d_half', (40, 21, 13), {}),
+         # binary16 pairs (H2): two cells per HADD2 / HMUL2
+         ('jacobi2d_half', (300, 37), {}),
+         ('jacobi2d_half', (280, 33), {'time_block': 2}),
+         ('jacobi2d_half', (150, 30), {'time_block': 2,
+                                       'options': {'no_pack': True}}),
+         # 3-D plans are unpacked by default; pairs on request
+         ('jacobi3d_half', (60, 21, 11), {'time_block': 2}),
+         ('jacobi3d_half', (60, 19, 12), {'time_block': 2,
+                                          'options': {'pack': True}})]
 
 
 def stencil(name, **overrides):
@@ -45,9 +54,25 @@ def test_type_rules():
     assert str(ir.common_type(ir.Type(other), half)) == want
   st = stencil('smooth2d_half')
   assert str(sodac.compile_source(str(st))) == str(st)
-  # 16-bit cells: eight per lane, never the packed fp32 path
+  # 16-bit cells: eight per lane; a division and a float literal keep the
+  # scalar path
   p = plan.make_tuned_pass_plan(st, 2)
   assert p.cells == 8 and p.pack == 1
+  assert not plan.packable(st)
+
+
+def test_half_pairs_are_planned_for_add_sub_mul_programs():
+  st = stencil('jacobi2d_half')
+  assert plan.packable(st)
+  p = plan.make_tuned_pass_plan(st, 2)
+  assert p.cells == 8 and p.pack == 2
+  assert plan.make_tuned_pass_plan(st, 2, {'no_pack': True}).pack == 1
+  # `* 0.2f` is a float multiplication of the converted sum: not a half pair
+  text = open(os.path.join(EXTRA, 'jacobi2d_half.soda')).read()
+  assert not plan.packable(sodac.compile_source(
+      text.replace('half(0.2f)', '0.2f')))
+  # an integer literal converts to half and is broadcast
+  assert plan.packable(sodac.compile_source(text.replace('half(0.2f)', '3')))
 
 
 def test_every_operation_rounds_once():
@@ -104,6 +129,12 @@ def test_under_emulation(name, extent, kwargs):
     ('smooth2d_half', (1000, 211), {'time_block': 2}),
     ('smooth2d_half', (333, 90), {}),
     ('mix3d_half', (150, 45, 21), {}),
+    ('jacobi2d_half', (1000, 300), {'time_block': 2}),
+    ('jacobi2d_half', (2000, 150), {'time_block': 2,
+                                    'options': {'no_pack': True}}),
+    ('jacobi3d_half', (300, 40, 30), {'time_block': 2}),
+    ('jacobi3d_half', (300, 40, 30), {'time_block': 2,
+                                      'options': {'pack': True}}),
 ])
 def test_on_gpu(name, extent, kwargs):
   from soda_b200.codegen import cuda as cuda_backend
