@@ -462,8 +462,7 @@ def make_tuned_pass_plan(stencil, time_block: int,
 
   * 2-D: 8 fp32 cells per lane instead of 4 (half the strip overlap and half
     the shuffles per cell) while the register windows stay below ~160
-    registers; pipelined schedule.  (16-bit cells stay at 8 per lane: a warp's
-    strip is one TMA box, at most 256 elements wide.)
+    registers; pipelined schedule.
   * 3-D: unpacked arithmetic; as many patch rows per thread (4, 2, 1) as keep
     the windows below ~120 registers; tile rows = 4 x the dimension-1 halo,
     at least 8 - small CTAs, several per SM, hide the per-step barrier better
@@ -479,6 +478,11 @@ def make_tuned_pass_plan(stencil, time_block: int,
   window = sum(n.ring * max(1, n.haoda_type.width_in_bits // 32)
                for n in probe.nodes)
   if dim == 2:
+    # 8- and 16-bit cells stay at 8 per lane.  16-cell lanes work (`cells`
+    # option; the 512-cell strip then arrives as two TMA boxes) but measured
+    # slower on B200 for every program tried: blur time block 2 1577 vs 1791
+    # Gcell-updates/s, sobel2d 1382 vs 1451, half jacobi2d time block 6 4368
+    # vs 4826 (profiles/r01_lanes16.jsonl)
     if cells is None and probe.cells * 2 * window <= 160 and all(
         t.width_in_bits == 32 for t in stencil.input_types +
         stencil.output_types + tuple(stencil.local_types)):

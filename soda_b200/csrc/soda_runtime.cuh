@@ -265,7 +265,7 @@ int launch_pass_2d(const PassArgs& a) {
 
   Params2D<Prog> p;
   memset(&p, 0, sizeof(p));
-  const int box[2] = {Prog::kStrip, Prog::kChunk};
+  const int box[2] = {S::kBox0, Prog::kChunk};  // S::kBoxes of them per strip
   int status = make_input_maps<Prog>(p.in_map, a, box);
   if (status != SODA_CUDA_OK) return status;
 

@@ -458,21 +458,42 @@ struct Params2D {
 template <class Prog>
 struct Smem2D {
   // per warp: kStages slots, each holding kChunk rows of every input strip,
-  // laid out [input][row][cell]
+  // laid out [input][box][row][cell]: a TMA box is at most 256 elements wide,
+  // so a 512-cell strip (16-cell lanes of 8- and 16-bit cells) arrives as two
+  // boxes side by side, lanes 0-15 reading the first and 16-31 the second
   static constexpr int kStages = Prog::kStages;
   static constexpr int kChunk = Prog::kChunk;
   static constexpr int kStrip = Prog::kStrip;
+  static constexpr int kBox0 = kStrip > 256 ? 256 : kStrip;
+  static constexpr int kBoxes = kStrip / kBox0;
+  static_assert(kStrip % kBox0 == 0 && kBox0 % Prog::kCells == 0,
+                "strip is whole boxes, a lane stays inside one box");
 
   template <int M>
   __host__ __device__ static constexpr int row_bytes() {
-    return int(sizeof(typename Prog::template T<M>)) * kStrip;
+    return int(sizeof(typename Prog::template T<M>)) * kBox0;
+  }
+  template <int M>
+  __host__ __device__ static constexpr int box_bytes() {
+    return row_bytes<M>() * kChunk;
   }
   template <int M>
   __host__ __device__ static constexpr int input_offset() {  // byte offset of input M in a slot
     if constexpr (M == 0) {
       return 0;
     } else {
-      return input_offset<M - 1>() + row_bytes<M - 1>() * kChunk;
+      return input_offset<M - 1>() + box_bytes<M - 1>() * kBoxes;
+    }
+  }
+  // byte offset of a lane's first cell in row 0 of input M
+  template <int M>
+  __device__ __forceinline__ static int lane_offset(int lane) {
+    const int col = lane * Prog::kCells;
+    if constexpr (kBoxes == 1) {
+      return col * int(sizeof(typename Prog::template T<M>));
+    } else {
+      return (col / kBox0) * box_bytes<M>() +
+             (col % kBox0) * int(sizeof(typename Prog::template T<M>));
     }
   }
   static constexpr int kSlotBytes = input_offset<Prog::kNumInputs>();
@@ -539,9 +560,9 @@ __device__ __forceinline__ void step_node_2d(Ctx& ctx, int t, int r) {
     using S = Smem2D<Prog>;
     const T* row = reinterpret_cast<const T*>(
         ctx.slot_base + S::template input_offset<M>() +
-        r * S::template row_bytes<M>());
+        r * S::template row_bytes<M>() + S::template lane_offset<M>(ctx.lane));
     T cells[Prog::kCells];
-    load_shared_vec<T, Prog::kCells>(cells, row + ctx.lane * Prog::kCells);
+    load_shared_vec<T, Prog::kCells>(cells, row);
     units_from_cells<Prog, N>(newest_units<N, 0, Prog>(ctx), cells);
   } else {
     eval_units<Prog, Ctx, N>(ctx);
@@ -567,8 +588,13 @@ __device__ __forceinline__ void issue_chunk_2d(const Params2D<Prog>& p,
                                                unsigned char* slot, int x0,
                                                int row, Mbarrier* bar) {
   if constexpr (M < Prog::kNumInputs) {
-    tma_load_2d(slot + Smem2D<Prog>::template input_offset<M>(), &p.in_map[M],
-                x0, row, bar);
+    using S = Smem2D<Prog>;
+#pragma unroll
+    for (int b = 0; b < S::kBoxes; ++b) {
+      tma_load_2d(slot + S::template input_offset<M>() +
+                      b * S::template box_bytes<M>(),
+                  &p.in_map[M], x0 + b * S::kBox0, row, bar);
+    }
     issue_chunk_2d<Prog, M + 1>(p, slot, x0, row, bar);
   }
 }

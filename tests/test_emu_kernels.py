@@ -41,6 +41,10 @@ CASES_2D = [
 ]
 CASES_2D.append(('jacobi2d', dict(extent=(300, 40), time_block=3, iterate=3,
                                   options={'no_pack': True})))
+# 16-cell lanes of 16-bit cells: the 512-cell strip is two TMA boxes side by
+# side (three strips at this width, the last one ragged)
+CASES_2D.append(('blur', dict(extent=(1300, 21), time_block=2, iterate=2,
+                              options={'cells': 16}, segment=8)))
 CASES_3D = [
     ('jacobi3d', dict(extent=(150, 21, 11), time_block=2, iterate=3,
                       options={'rows': 8}, segment=6)),

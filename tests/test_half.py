@@ -31,6 +31,8 @@ CASES = [('smooth2d_half', (150, 37), {}),
          # binary16 pairs (H2): two cells per HADD2 / HMUL2
          ('jacobi2d_half', (300, 37), {}),
          ('jacobi2d_half', (280, 33), {'time_block': 2}),
+         ('jacobi2d_half', (1100, 21), {'time_block': 2,
+                                        'options': {'cells': 16}}),
          ('jacobi2d_half', (150, 30), {'time_block': 2,
                                        'options': {'no_pack': True}}),
          # 3-D plans are unpacked by default; pairs on request
@@ -66,6 +68,9 @@ def test_half_pairs_are_planned_for_add_sub_mul_programs():
   assert plan.packable(st)
   p = plan.make_tuned_pass_plan(st, 2)
   assert p.cells == 8 and p.pack == 2
+  # 16-cell lanes on request: the 512-cell strip is two TMA boxes
+  wide = plan.make_tuned_pass_plan(st, 2, {'cells': 16})
+  assert wide.cells == 16 and wide.strip == 512 and wide.pack == 2
   assert plan.make_tuned_pass_plan(st, 2, {'no_pack': True}).pack == 1
   # `* 0.2f` is a float multiplication of the converted sum: not a half pair
   text = open(os.path.join(EXTRA, 'jacobi2d_half.soda')).read()
