@@ -173,20 +173,21 @@ def _min_blocks_3d(pass_plan: planner.PassPlan) -> int:
 
 
 def tuning_3d(pass_plan: planner.PassPlan, options: Dict) -> Dict[str, int]:
-  in_depth = max(
-      [1] + [n.smem_depth for n in pass_plan.nodes if n.kind == 'input'])
-  reach = 0
-  elem = 4
-  for node in pass_plan.nodes:
-    elem = max(elem, node.haoda_type.width_in_bits // 8)
-    for deltas in node.deltas:
-      for delta in deltas:
-        if delta[1] != 0:
-          reach = max(reach,
-                      abs(delta[1]) * pass_plan.strip + abs(delta[0]) +
-                      pass_plan.cells)
-  guard = (reach * elem + 127) // 128 * 128
-  stages = in_depth + (options.get('lookahead') or 2)
+  geometry = planner.smem_geometry_3d(pass_plan, options.get('lookahead') or 2)
+  in_depth = geometry['in_depth']
+  guard = geometry['guard']
+  stages = geometry['stages']
+  threads = pass_plan.rows // pass_plan.cy * 32
+  if threads > planner.MAX_CTA_THREADS:
+    raise util.SemanticError(
+        'a tile of %d rows with %d rows per thread needs %d threads per CTA '
+        '(at most %d): lower --cuda-tile rows or raise the rows per thread' %
+        (pass_plan.rows, pass_plan.cy, threads, planner.MAX_CTA_THREADS))
+  if geometry['bytes'] > planner.SMEM_LIMIT_BYTES:
+    raise util.SemanticError(
+        'a tile of %d rows needs %d bytes of shared memory per CTA (at most '
+        '%d): lower the tile rows or the time block' %
+        (pass_plan.rows, geometry['bytes'], planner.SMEM_LIMIT_BYTES))
   # unroll the step loop so that window rotation is register renaming and ring
   # slots are compile-time constants, unless the DAG is large (code size)
   rings = sorted({n.ring for n in pass_plan.nodes if n.ring > 1})
@@ -282,6 +283,12 @@ def _emit_pass(ns: str, stencil, pass_plan: planner.PassPlan,
   lines.append('  static constexpr int kReachHi[%d] = {%s};' %
                (dim, ', '.join(map(str, reach_hi))))
   lines.append('};')
+  if dim == 3:
+    # the planner sized the tile with its own copy of this arithmetic
+    lines.append('static_assert(soda::Smem3D<Prog>::kBytes == %d, "planner and '
+                 'template disagree on the shared-memory footprint");' %
+                 planner.smem_geometry_3d(
+                     pass_plan, options.get('lookahead') or 2)['bytes'])
   lines.append('}  // namespace %s' % ns)
   return lines
 

@@ -453,6 +453,40 @@ def make_pass_plan(stencil,
                   skew=step_skew)
 
 
+# dynamic shared memory one CTA may ask for on sm_100a (227 KB)
+SMEM_LIMIT_BYTES = 227 * 1024
+MAX_CTA_THREADS = 1024
+
+
+def smem_geometry_3d(pass_plan: PassPlan, lookahead: int = 2) -> Dict[str, int]:
+  """Shared-memory footprint of a 3-D pass, the arithmetic of Smem3D in
+  soda_stream.cuh: a TMA ring of ``stages`` slots (one plane per input each),
+  ``smem_depth`` exported planes per fused stage that is read across tile rows,
+  guard bytes on both sides, the barriers."""
+  in_depth = max(
+      [1] + [n.smem_depth for n in pass_plan.nodes if n.kind == 'input'])
+  reach = 0
+  elem = 4
+  for node in pass_plan.nodes:
+    elem = max(elem, node.haoda_type.width_in_bits // 8)
+    for deltas in node.deltas:
+      for delta in deltas:
+        if delta[1] != 0:
+          reach = max(reach,
+                      abs(delta[1]) * pass_plan.strip + abs(delta[0]) +
+                      pass_plan.cells)
+  guard = (reach * elem + 127) // 128 * 128
+  stages = in_depth + lookahead
+  plane_cells = pass_plan.strip * pass_plan.rows
+  slot = sum(n.haoda_type.width_in_bits // 8 * plane_cells
+             for n in pass_plan.nodes if n.kind == 'input')
+  exports = sum(n.smem_depth * (n.haoda_type.width_in_bits // 8) * plane_cells
+                for n in pass_plan.nodes if n.kind == 'stage')
+  barriers = (guard + slot * stages + exports + guard + 127) // 128 * 128
+  return {'in_depth': in_depth, 'guard': guard, 'stages': stages,
+          'bytes': barriers + 8 * stages}
+
+
 def make_tuned_pass_plan(stencil, time_block: int,
                          options: Optional[Dict] = None) -> PassPlan:
   """``make_pass_plan`` with the launch shape chosen from the DAG.
@@ -511,6 +545,16 @@ def make_tuned_pass_plan(stencil, time_block: int,
     # Gcell-updates/s)
     rows = max(8, (6 if cy == 1 else 4) * halo)
     rows = _round_up(rows, cy)
+    # a CTA has rows / cy warps and its planes must fit shared memory: deep
+    # multi-input DAGs (several exported stages, wide dimension-1 halos) get
+    # a lower tile, down to one patch row more than the halo
+    rows = min(rows, MAX_CTA_THREADS // 32 * cy)
+    while rows - cy > halo:
+      trial = make_pass_plan(stencil, time_block=time_block, cells=cells,
+                             rows=rows, cy=cy, pack=pack, pipelined=pipelined)
+      if smem_geometry_3d(trial)['bytes'] <= SMEM_LIMIT_BYTES:
+        return trial
+      rows -= cy
   return make_pass_plan(stencil, time_block=time_block, cells=cells, rows=rows,
                         cy=cy, pack=pack, pipelined=pipelined)
 

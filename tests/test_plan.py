@@ -1,7 +1,7 @@
 """Planner tables: lags, register-window depths, halos, pass schedule."""
 import pytest
 
-from soda_b200 import util
+from soda_b200 import sodac, util
 from soda_b200.codegen.cuda import emit, plan
 from tests import common
 
@@ -163,3 +163,27 @@ def test_patch_rows_export_only_their_edges():
   assert mid.ring == 3 and t1.ring == 3
   with pytest.raises(util.SemanticError):
     plan.make_pass_plan(common.stencil('jacobi3d'), rows=10, cy=4)
+
+
+def test_3d_tiles_fit_shared_memory_and_the_thread_limit():
+  """Found by tests/test_random_programs.py seed 13 on B200: two half inputs
+  and two exported stages with a dimension-1 halo of 5 rows asked for a 30-row
+  tile = 276 KB of shared memory.  The tuned plan lowers the tile until it
+  fits; explicit oversize requests fail at compile time, not at launch."""
+  from tests import random_programs
+  text, _, _ = random_programs.program(13)
+  st = sodac.compile_source(text)
+  tuned = plan.make_tuned_pass_plan(st, 1)
+  geometry = plan.smem_geometry_3d(tuned)
+  assert geometry['bytes'] <= plan.SMEM_LIMIT_BYTES
+  assert tuned.rows // tuned.cy * 32 <= plan.MAX_CTA_THREADS
+  assert tuned.rows > tuned.halo_lo[1] + tuned.halo_hi[1]
+  with pytest.raises(util.SemanticError, match='shared memory'):
+    emit.emit_program(st, options={'rows': 32})
+  with pytest.raises(util.SemanticError, match='threads per CTA'):
+    emit.emit_program(common.stencil('jacobi3d'), options={'rows': 40, 'cy': 1})
+  # the programs of tests/src keep their measured tiles
+  jacobi = plan.make_tuned_pass_plan(common.stencil('jacobi3d', iterate=4), 2)
+  assert (jacobi.rows, jacobi.cy) == (16, 4)
+  denoise = plan.make_tuned_pass_plan(common.stencil('denoise3d'), 1)
+  assert (denoise.rows, denoise.cy) == (24, 1)
