@@ -285,10 +285,10 @@ def _emit_pass(ns: str, stencil, pass_plan: planner.PassPlan,
   lines.append('};')
   if dim == 3:
     # the planner sized the tile with its own copy of this arithmetic
-    lines.append('static_assert(soda::Smem3D<Prog>::kBytes == %d, "planner and '
-                 'template disagree on the shared-memory footprint");' %
-                 planner.smem_geometry_3d(
-                     pass_plan, options.get('lookahead') or 2)['bytes'])
+    lines.append('static_assert(soda::Smem3D<Prog>::kBarrierOffset == %d, '
+                 '"planner and template disagree on the shared-memory '
+                 'footprint");' % planner.smem_geometry_3d(
+                     pass_plan, options.get('lookahead') or 2)['barrier_offset'])
   lines.append('}  // namespace %s' % ns)
   return lines
 

@@ -484,7 +484,7 @@ def smem_geometry_3d(pass_plan: PassPlan, lookahead: int = 2) -> Dict[str, int]:
                 for n in pass_plan.nodes if n.kind == 'stage')
   barriers = (guard + slot * stages + exports + guard + 127) // 128 * 128
   return {'in_depth': in_depth, 'guard': guard, 'stages': stages,
-          'bytes': barriers + 8 * stages}
+          'barrier_offset': barriers, 'bytes': barriers + 8 * stages}
 
 
 def make_tuned_pass_plan(stencil, time_block: int,

@@ -90,13 +90,12 @@ def lower_text(text: str) -> str:
 
     return expr.visit(callback)
 
-  lines = []
-  for line in str(program).split('\n'):
-    lines.append(line)
   # statements are rebuilt one by one so that the header is kept verbatim
-  header = [l for l in str(program).split('\n')
-            if not l.startswith(('input ', 'param ', 'local ', 'output '))]
-  out = [l for l in header if l.strip()]
+  # (directives start in column 0; the indented lines are the let bindings
+  # and the stored expression of a multi-line statement)
+  out = [l for l in str(program).split('\n')
+         if l.strip() and not l[0].isspace() and
+         not l.startswith(('input ', 'param ', 'local ', 'output '))]
   for stmt in program.input_stmts + program.param_stmts:
     if is_narrow(stmt.haoda_type):
       stmt = stmt.visit(lambda obj, args: obj)

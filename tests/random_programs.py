@@ -94,25 +94,37 @@ def _int_expr(rng, sources, dim, reach, taps, store):
   return '((%s) ^ (%s & 5) | 1) %% 2003' % (expr, terms[0])
 
 
-def program(seed: int):
-  rng = np.random.default_rng(1000 + seed)
+def program(seed: int, hard: bool = False):
+  """``hard``: wider windows (up to 4 cells in dimension 0), up to four local
+  stages whose types differ from the tensors' (a double stage in a half
+  program, an int32 stage between uint8 ones), ``let`` bindings, three inputs,
+  double and 64-bit integer tensors.  The test-suite pins the plain seeds;
+  tools/random_sweep.py explores the hard ones."""
+  rng = np.random.default_rng((5000 if hard else 1000) + seed)
   dim = 2 if rng.random() < 0.65 else 3
   floating = rng.random() < 0.55
-  family = (FLOAT_FAMILIES if floating else INT_FAMILIES)[int(
-      rng.integers(len(FLOAT_FAMILIES if floating else INT_FAMILIES)))]
+  float_families = FLOAT_FAMILIES + (('double',) if hard else ())
+  int_families = INT_FAMILIES + (('int64',) if hard else ())
+  family = (float_families if floating else int_families)[int(
+      rng.integers(len(float_families if floating else int_families)))]
   # reach per dimension: dimension 0 costs shuffles, dimension 1 shared memory
   # (3-D) or register rows (2-D), the last one window depth
   reach = [int(rng.integers(0, 3)) for _ in range(dim)]
+  if hard:
+    reach[0] = int(rng.integers(0, 5))
+    if dim == 2:
+      reach[1] = int(rng.integers(0, 4))
   if not any(reach):
     reach[int(rng.integers(dim))] = 1
   num_inputs = 1 if rng.random() < 0.7 else 2
-  num_locals = int(rng.integers(0, 3))
+  if hard and rng.random() < 0.2:
+    num_inputs = 3
+  num_locals = int(rng.integers(0, 5 if hard else 3))
   iterate = 1
   if num_inputs == 1 and rng.random() < 0.6:
     iterate = int(rng.integers(2, 4))
   tile = ', '.join(['32'] * (dim - 1) + ['*'])
 
-  local_family = family
   lines = ['kernel: rnd%d' % seed, 'burst width: 64', 'unroll factor: 2',
            'iterate: %d' % iterate]
   inputs = ['in%d' % i for i in range(num_inputs)]
@@ -124,11 +136,32 @@ def program(seed: int):
     name = 'loc%d' % k
     taps = int(rng.integers(2, 5))
     store = _idx(rng, dim, [1] * dim) if rng.random() < 0.25 else (0,) * dim
+    local_family = family
+    if hard and rng.random() < 0.4:
+      pool = float_families if floating else ('int16', 'int32', 'uint16',
+                                              'int64')
+      local_family = pool[int(rng.integers(len(pool)))]
     if floating:
       expr = _float_expr(rng, local_family, sources, dim, reach, taps, store)
     else:
       expr = _int_expr(rng, sources, dim, reach, taps, store)
-    lines.append('local %s: %s = %s' % (local_family, _ref(name, store), expr))
+    if hard and rng.random() < 0.4:
+      # a typed and an untyped let, used twice
+      first = _ref(sources[int(rng.integers(len(sources)))], store)
+      other = _ref(sources[0], _idx(rng, dim, reach, store))
+      if floating:
+        lets = ('\n  %s t = %s * 0.5f\n  u = t - %s * t\n  ' %
+                (local_family, first, other))
+        expr = '(%s) * 0.5f + u * 0.25f - t * u * 0.125f' % expr
+      else:
+        lets = ('\n  int32 t = (%s + %s) / 2\n  u = t - %s\n  ' %
+                (first, other, first))
+        expr = '((%s) + (t & 255) - (u %% 7)) %% 4093' % expr
+      lines.append('local %s:%s%s = %s' % (local_family, lets,
+                                          _ref(name, store), expr))
+    else:
+      lines.append('local %s: %s = %s' % (local_family, _ref(name, store),
+                                          expr))
     sources.append(name)
   taps = int(rng.integers(2, 6))
   # the output reads the newest stages preferentially so that the DAG is deep

@@ -169,3 +169,35 @@ def test_narrow_widths_on_gpu():
   prog.run_host(inputs, outputs)
   common.assert_matches_oracle(st, extent, outputs,
                                emit_cpp.Oracle(st).run(inputs), sentinel=77)
+
+
+def test_narrow_widths_with_let_bindings():
+  """Found by the random-program sweep: the let lines of a multi-line
+  statement must not leak into the header of the lowered program."""
+  from soda_b200.optimization import widths
+  st = sodac.compile_source('''kernel: narrowlet
+burst width: 64
+unroll factor: 2
+iterate: 2
+input uint6: a(32, *)
+local uint6:
+  int32 t = (a(0, 0) + a(1, -1)) / 2
+  u = t - a(0, 1)
+  m(0, 0) = (t & 255) - (u % 7) + a(-1, 0)
+output uint6: b(0, 0) = (m(0, 0) + m(1, 1) + a(0, 0)) * 3 % 17
+''')
+  low = widths.lower(st)
+  assert not widths.has_narrow_types(low)
+  assert [str(l.name) for l in low.local_stmts[0].let] == ['t', 'u']
+  extent = (70, 19)
+  inputs = _narrow_inputs(st, extent)
+  a = golden.run(st, inputs)
+  b = emit_cpp.Oracle(st).run(inputs)
+  c = golden.run(low, inputs)
+  index = common.box_index(st.valid_box('b', extent))
+  assert np.array_equal(a['b'][index], b['b'][index])
+  assert np.array_equal(a['b'][index], c['b'][index])
+  prog = launcher.CudaProgram(build_emu.build_emu_library(st))
+  outputs = {'b': np.full(extent[::-1], 77, dtype=np.uint8)}
+  prog.run_host(inputs, outputs)
+  common.assert_matches_oracle(st, extent, outputs, b, sentinel=77)

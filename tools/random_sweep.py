@@ -4,6 +4,8 @@
 
   python tools/random_sweep.py build 40 120   # compile (no GPU needed)
   python tools/random_sweep.py run 40 120     # one JSON line per seed
+  ... --hard: the generator's hard mode (wider windows, deeper DAGs, mixed
+  stage types, let bindings, double / int64)
 """
 import concurrent.futures
 import json
@@ -21,8 +23,11 @@ from soda_b200.codegen.cuda import launcher  # noqa: E402
 from tests import common, random_programs  # noqa: E402
 
 
+HARD = '--hard' in sys.argv
+
+
 def build_one(seed):
-  text, _, kwargs = random_programs.program(seed)
+  text, _, kwargs = random_programs.program(seed, hard=HARD)
   try:
     return cuda_build.build_library(sodac.compile_source(text),
                                     kwargs.get('time_block'),
@@ -33,7 +38,7 @@ def build_one(seed):
 
 def run_one(seed):
   from oracle import emit_cpp, golden
-  text, extent, kwargs = random_programs.program(seed)
+  text, extent, kwargs = random_programs.program(seed, hard=HARD)
   st = sodac.compile_source(text)
   inputs = random_programs.inputs_for(st, extent, seed)
   lib = build_one(seed)
