@@ -215,3 +215,33 @@ def inputs_for(st, extent, seed):
     else:
       result[stmt.name] = rng.integers(0, 2048, shape).astype(dtype)
   return result
+
+
+def sum_program(seed: int):
+  """A one-stage sum of 4-11 taps drawn from a small box: the shape
+  computation reuse rewrites.  Returns (text, extent, number of taps).  Integer
+  programs make the rewrite checkable exactly (modular addition is associative
+  and commutative), float ones within rounding."""
+  rng = np.random.default_rng(7000 + seed)
+  dim = 2 if rng.random() < 0.7 else 3
+  t = ('int32', 'int16', 'float', 'uint16')[int(rng.integers(4))]
+  box = [int(rng.integers(1, 3)) for _ in range(dim)]
+  points = {(0,) * dim}
+  capacity = 1
+  for b in box:
+    capacity *= 2 * b + 1
+  taps = min(int(rng.integers(4, 12)), capacity)
+  while len(points) < taps:
+    points.add(tuple(int(rng.integers(-b, b + 1)) for b in box))
+  refs = ' + '.join(_ref('a', p) for p in sorted(points))
+  tile = ', '.join(['32'] * (dim - 1) + ['*'])
+  text = ('kernel: cr%d\nburst width: 64\nunroll factor: 2\niterate: %d\n'
+          'input %s: a(%s)\noutput %s: %s = (%s) %s\n' %
+          (seed, int(rng.integers(1, 3)), t, tile, t, _ref('b', (0,) * dim),
+           refs, '* 0.1f' if t == 'float' else '/ 3'))
+  if dim == 2:
+    extent = (int(rng.integers(40, 120)), int(rng.integers(20, 40)))
+  else:
+    extent = (int(rng.integers(40, 90)), int(rng.integers(20, 30)),
+              int(rng.integers(16, 24)))
+  return text, extent, len(points)

@@ -69,3 +69,41 @@ def test_on_gpu(seed):
   from soda_b200.codegen import cuda as cuda_backend
   st, extent, kwargs, inputs = _case(seed)
   _check(st, extent, cuda_backend.compile_stencil(st, **kwargs), inputs)
+
+
+# ---- computation reuse on random sum stencils --------------------------------------
+
+@pytest.mark.parametrize('seed', range(16))
+def test_computation_reuse_keeps_the_value(seed):
+  """Every scheduler (native soda-cr contract, greedy, built-in) must return a
+  program that computes the same sums with no more additions: exactly for
+  integer tensors, within rounding for float ones."""
+  text, extent, taps = random_programs.sum_program(seed)
+  plain = sodac.compile_source(text)
+  inputs = random_programs.inputs_for(plain, extent, seed)
+  want = golden.run(plain, inputs)['b']
+  index = common.box_index(plain.valid_box('b', extent))
+  for mode in ('yes', 'greedy', 'built-in'):
+    reused = sodac.compile_source(text, computation_reuse=mode)
+    assert reused.valid_box('b', extent) == plain.valid_box('b', extent)
+    assert str(reused).count(' + ') <= taps - 1
+    got = golden.run(reused, inputs)['b']
+    if plain.input_types[0].is_float:
+      assert np.allclose(want[index], got[index], rtol=1e-5, atol=1e-6)
+    else:
+      assert np.array_equal(want[index], got[index])
+
+
+@pytest.mark.parametrize('seed', [0, 3, 8, 16])
+def test_computation_reuse_under_emulation(seed):
+  """The rewritten program (shared partial sums as fused local stages) through
+  the CUDA templates, bit-exact against its own golden loops."""
+  text, extent, _ = random_programs.sum_program(seed)
+  st = sodac.compile_source(text, computation_reuse='yes')
+  inputs = random_programs.inputs_for(st, extent, seed)
+  prog = launcher.CudaProgram(build_emu.build_emu_library(st))
+  dtype = golden.np_dtype(st.output_stmts[0].haoda_type)
+  outputs = {'b': np.full(extent[::-1], 77, dtype=dtype)}
+  prog.run_host(inputs, outputs)
+  common.assert_matches_oracle(st, extent, outputs,
+                               emit_cpp.Oracle(st).run(inputs), sentinel=77)
