@@ -276,8 +276,11 @@ def _emit_pass(ns: str, stencil, pass_plan: planner.PassPlan,
   out_nodes = sorted(pass_plan.output_nodes, key=lambda n: n.out)
   lines.append('  static constexpr int kOutputNode[kNumOutputs] = {%s};' %
                ', '.join(str(n.id) for n in out_nodes))
-  reach_lo = [min(n.win_lo[d] for n in out_nodes) for d in range(dim)]
-  reach_hi = [max(n.win_hi[d] for n in out_nodes) for d in range(dim)]
+  # the ABI promises reach_lo <= 0 <= reach_hi (include/soda_cuda.h): a window
+  # that lies strictly on one side of the stored cell still spans the cell
+  # itself as far as chunking and halo exchange are concerned
+  reach_lo = [min(0, min(n.win_lo[d] for n in out_nodes)) for d in range(dim)]
+  reach_hi = [max(0, max(n.win_hi[d] for n in out_nodes)) for d in range(dim)]
   lines.append('  static constexpr int kReachLo[%d] = {%s};' %
                (dim, ', '.join(map(str, reach_lo))))
   lines.append('  static constexpr int kReachHi[%d] = {%s};' %

@@ -80,8 +80,10 @@ class SlabRunner:
     self.ranges = split_slices(total, self.world)
     self.begin, self.end = self.ranges[self.rank]
     infos = [program.pass_info(i) for i in range(program.num_passes)]
-    self.pass_reach = [(-info.reach_lo[s_dim], info.reach_hi[s_dim])
-                       for info in infos]
+    # clamped: a window strictly on one side of the stored cell reaches 0
+    # slices the other way, never a negative number
+    self.pass_reach = [(max(0, -info.reach_lo[s_dim]),
+                        max(0, info.reach_hi[s_dim])) for info in infos]
     slab = min(end - begin for begin, end in self.ranges)
     self.groups = self._make_groups(exchange_every, slab)
     # ghost depth: what the deepest group needs before its first pass

@@ -604,8 +604,9 @@ inline int run_passes_window(soda_cuda_plan* plan, const void* const* d_in,
   int reach_lo = 0, reach_hi = 0;
   for (int pass = 0; pass < num_passes; ++pass) {
     const soda_cuda_pass_info& info = prog.impls[prog.schedule[pass]].info;
-    reach_lo += -info.reach_lo[s_dim];
-    reach_hi += info.reach_hi[s_dim];
+    // one-sided windows: a pass never reaches less than its own slice
+    reach_lo += std::max(0, -info.reach_lo[s_dim]);
+    reach_hi += std::max(0, info.reach_hi[s_dim]);
   }
   const int total = plan->extent[s_dim];
   const int view_lo = s_begin - reach_lo > 0 ? s_begin - reach_lo : 0;
@@ -927,7 +928,7 @@ int soda_cuda_plan_run_host(soda_cuda_plan* plan, const void* const* in_ptrs,
   int reach = 0;
   for (int pass = 0; pass < prog.info.num_passes; ++pass) {
     const soda_cuda_pass_info& info = prog.impls[prog.schedule[pass]].info;
-    reach += info.reach_hi[s_dim] - info.reach_lo[s_dim];
+    reach += std::max(0, info.reach_hi[s_dim]) + std::max(0, -info.reach_lo[s_dim]);
   }
   long long bytes = 0;
   for (int i = 0; i < prog.info.num_inputs; ++i)
@@ -1010,7 +1011,8 @@ int soda_cuda_plan_run_host(soda_cuda_plan* plan, const void* const* in_ptrs,
   }
   int reach_hi_total = 0;
   for (int pass = 0; pass < prog.info.num_passes; ++pass)
-    reach_hi_total += prog.impls[prog.schedule[pass]].info.reach_hi[s_dim];
+    reach_hi_total +=
+        std::max(0, prog.impls[prog.schedule[pass]].info.reach_hi[s_dim]);
   for (int k = 0; k < chunks && result == SODA_CUDA_OK; ++k) {
     // the window of chunk k ends at bound[k+1] + reach_hi: wait for the last
     // chunk it touches (copies are issued in order on one stream)

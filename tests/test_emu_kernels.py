@@ -97,3 +97,52 @@ def test_pipelined_host_path_under_emulation(name, kwargs):
   """soda_cuda_plan_run_host cuts the grid into overlapping chunks along the
   streamed dimension so that copies overlap compute; results must not change."""
   run_case(name, host_chunks=3, **kwargs)
+
+
+ONE_SIDED_2D_NEG = '''kernel: one_sided_neg
+burst width: 64
+unroll factor: 2
+iterate: 2
+input float: a(32, *)
+output float: b(0, 0) = (a(-1, -2) + a(-2, -1)) * 0.5f
+'''
+ONE_SIDED_2D_POS = '''kernel: one_sided_pos
+burst width: 64
+unroll factor: 2
+iterate: 3
+input int32: a(32, *)
+output int32: b(0, 0) = (a(1, 2) + a(2, 1)) / 2
+'''
+ONE_SIDED_3D = '''kernel: one_sided_3d
+burst width: 64
+unroll factor: 2
+iterate: 2
+input float: a(32, 32, *)
+output float: b(0, 0, 0) = (a(0, 1, 2) + a(1, 0, 1)) * 0.5f
+'''
+
+
+@pytest.mark.parametrize('text,extent', [(ONE_SIDED_2D_NEG, (70, 36)),
+                                         (ONE_SIDED_2D_POS, (70, 36)),
+                                         (ONE_SIDED_3D, (40, 12, 20))])
+@pytest.mark.parametrize('host_chunks', [1, 3])
+def test_one_sided_windows_over_several_passes(text, extent, host_chunks):
+  """A window that lies strictly on one side of the stored cell in the
+  streamed dimension: the pass reach the runtime sums over the passes (chunk
+  windows, halo depths) must never go negative.  iterate > time_block, so
+  intermediates travel through the scratch arrays."""
+  from soda_b200 import sodac
+  st = sodac.compile_source(text)
+  prog = launcher.CudaProgram(
+      build_emu.build_emu_library(st, time_block=1, options={'rows': 8}
+                                  if st.dim == 3 else None))
+  for index in range(prog.num_passes):
+    info = prog.pass_info(index)
+    assert all(lo <= 0 <= hi for lo, hi in zip(info.reach_lo, info.reach_hi))
+  inputs = common.make_inputs(st, extent, seed=3)
+  outputs = {n: np.full(extent[::-1], 77, dtype=d)
+             for n, d in zip(prog.output_names, prog.output_dtypes)}
+  prog.run_host(inputs, outputs,
+                opts=launcher.make_opts(host_chunks=host_chunks))
+  common.assert_matches_oracle(st, extent, outputs,
+                               common.oracle_outputs(st, inputs), sentinel=77)
