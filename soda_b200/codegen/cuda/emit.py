@@ -309,7 +309,7 @@ def emit_program(stencil,
   # integer widths C++ does not have become containers + explicit wraps
   stencil = widths.lower(stencil)
   dim = stencil.dim
-  time_block = planner.choose_time_block(stencil, time_block)
+  time_block = planner.choose_time_block(stencil, time_block, options)
   schedule = planner.pass_schedule(stencil.iterate, time_block)
   variants = sorted(set(schedule), reverse=True)
   plans = {

@@ -559,14 +559,20 @@ def make_tuned_pass_plan(stencil, time_block: int,
                         cy=cy, pack=pack, pipelined=pipelined)
 
 
-def choose_time_block(stencil, requested: Optional[int] = None) -> int:
-  """Default temporal blocking: fuse up to 4 iterations for chain programs."""
+def choose_time_block(stencil, requested: Optional[int] = None,
+                      options: Optional[Dict] = None) -> int:
+  """Iterations fused per HBM round trip.  An explicit request wins; otherwise
+  the throughput model (model.py: HBM, FMA-pipe and issue ceilings against the
+  halo growth and the register windows of every candidate) picks it - the
+  counterpart of the reference's performance model, which sizes ``iterate``
+  the same way (reference: src/soda/model/xilinx.py:131-144)."""
   if stencil.iterate == 1 or len(stencil.input_stmts) != len(
       stencil.output_stmts):
     return 1
   if requested:
     return max(1, min(requested, stencil.iterate))
-  return min(stencil.iterate, 4 if stencil.dim == 2 else 2)
+  from soda_b200.codegen.cuda import model  # model imports this module
+  return model.choose_time_block(stencil, options)
 
 
 def pass_schedule(iterate: int, time_block: int) -> List[int]:
