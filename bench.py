@@ -460,9 +460,10 @@ def run_device_config(key, device, stream, steps, warmup, peak, windows=8):
 # ---------------------------------------------------------------------------
 # host <-> device copy peak of this box (the ceiling of e2e)
 # ---------------------------------------------------------------------------
-def measure_copy_peak(device, mib=256, reps=3):
+def measure_copy_peak(device, mib=256, reps=3, barrier=None):
   """GB/s of pinned host <-> device copies on this GPU: each direction alone
-  and both at once (two streams)."""
+  and both at once (two streams).  With ``barrier`` (N > 1) all ranks copy at
+  the same time, so the figures are what the box gives N GPUs together."""
   import torch
   n = (mib << 20) // 4
   h_a = torch.empty(n, dtype=torch.float32).pin_memory()
@@ -476,6 +477,8 @@ def measure_copy_peak(device, mib=256, reps=3):
     best = None
     for rep in range(reps + 1):
       torch.cuda.synchronize()
+      if barrier is not None:
+        barrier()
       t0 = time.perf_counter()
       if mode in ('h2d', 'both'):
         with torch.cuda.stream(s_in):
@@ -528,6 +531,13 @@ def run_ours(args, out):
       return x
     t = torch.tensor([x], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+  def sum_over_ranks(x):
+    if world == 1:
+      return x
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
 
   def gather_parity(report):
@@ -612,10 +622,11 @@ def run_ours(args, out):
   if args.no_e2e:
     pass
   elif world == 1:
-    h_in = torch.empty((HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
-    h_in.copy_(d_in)
-    h_out = torch.zeros((HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
-    np_in, np_out = h_in.numpy(), h_out.numpy()
+    pinned_in = launcher.HostBuffer(prog, (HEIGHT, WIDTH), np.float32, local_rank)
+    pinned_out = launcher.HostBuffer(prog, (HEIGHT, WIDTH), np.float32,
+                                     local_rank)
+    np_in, np_out = pinned_in.array, pinned_out.array
+    torch.from_numpy(np_in).copy_(d_in)
     e2e_steps = max(1, min(args.steps, 5))
     plan.run_host({'t1': np_in}, {'t0': np_out})  # warm-up (allocations)
     torch.cuda.synchronize()
@@ -635,7 +646,7 @@ def run_ours(args, out):
         'h2d_bytes_per_step': cells_per_gpu * 4,
         'd2h_bytes_per_step': d2h,
         'ms_per_step': e2e_s * 1e3,
-        'host_memory': 'pinned',
+        'host_memory': 'pinned (soda_cuda_host_alloc)',
         'api': 'soda_cuda_plan_run_host (chunked H2D / passes / D2H pipeline)',
         # the ceiling of this number: both copies at once on this box
         'pcie_peak_gbs': copy_peak['both_gbs'],
@@ -653,39 +664,80 @@ def run_ours(args, out):
       from oracle import cone
       e2e['parity'] = cone_parity(
           st, global_extent, cone.host_reader({'t0': np_out}), 8, seed=11)
-    del h_in, h_out, np_in, np_out
+    del np_in, np_out
+    pinned_in.close()
+    pinned_out.close()
   else:
-    # N > 1: every rank stages its own slab through pinned memory
-    lo, hi = runner.own
-    own = runner.view(runner.inputs[0])[lo:hi]
-    h_in = torch.empty(own.shape, dtype=torch.float32).pin_memory()
-    h_in.copy_(own)
-    h_out = torch.empty(own.shape, dtype=torch.float32).pin_memory()
-    e2e_steps = max(1, min(args.steps, 3))
+    # N > 1: every rank's own slab in pinned host memory, through the slab's
+    # chunked H2D / passes / D2H pipeline; the input ghosts (the total reach of
+    # all passes) come from the neighbours' uploads over NVLink, once per step
+    del runner
+    torch.cuda.empty_cache()
+    host_runner = multi_gpu.SlabRunner(prog, global_extent, device, rank=rank,
+                                       world=world, stream_handle=stream,
+                                       exchange_every=-1)
+    rows = host_runner.end - host_runner.begin
+    pinned_in = launcher.HostBuffer(prog, (rows, WIDTH), np.float32, local_rank)
+    pinned_out = launcher.HostBuffer(prog, (rows, WIDTH), np.float32,
+                                     local_rank)
+    np_in, np_out = pinned_in.array, pinned_out.array
+    staging = torch.empty((rows, WIDTH), dtype=torch.float32, device=device)
+    fill_synthetic(staging, host_runner.begin, 0, WIDTH)
+    torch.from_numpy(np_in).copy_(staging)
+    del staging
+    e2e_steps = max(1, min(args.steps, 5))
+    host_runner.run_host({'t1': np_in}, {'t0': np_out})  # warm-up
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-      own.copy_(h_in, non_blocking=True)
-      runner.run()
-      h_out.copy_(runner.view(runner.outputs[0])[lo:hi], non_blocking=True)
-      torch.cuda.synchronize()
+      host_runner.run_host({'t1': np_in}, {'t0': np_out})
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    copy_peak = measure_copy_peak(device, barrier=barrier)
+    peak_all = sum_over_ranks(copy_peak['both_gbs'])
+    nbytes = cells_per_gpu * 4 * world * 2
     e2e = {
         'value': cells_per_gpu * world * ITERATE / e2e_s / 1e9,
         'unit': 'Gcell-updates/s',
         'h2d_bytes_per_step': cells_per_gpu * 4 * world,
         'd2h_bytes_per_step': cells_per_gpu * 4 * world,
         'ms_per_step': e2e_s * 1e3,
-        'host_memory': 'pinned',
+        'host_memory': 'pinned (soda_cuda_host_alloc), one slab per rank',
+        'api': 'soda_cuda_slab_run_host (per-rank chunked H2D / passes / D2H '
+               'pipeline, one NVLink halo exchange per step)',
+        # all ranks copying both ways at the same time on this box
+        'pcie_peak_gbs': peak_all,
+        'achieved_gbs': nbytes / e2e_s / 1e9,
+        'frac': nbytes / e2e_s / 1e9 / peak_all,
     }
-    del h_in, h_out
+    if not args.no_parity:
+      from oracle import cone
+      required = []
+      if rank > 0:
+        required.append((WIDTH // 2, host_runner.begin))
+      if rank < world - 1:
+        required.append((WIDTH // 2, host_runner.end - 64))
+
+      def read_host(name, box, origin=host_runner.begin):
+        del name
+        return np_out[box[1][0] - origin:box[1][1] - origin,
+                      box[0][0]:box[0][1]]
+
+      e2e['parity'] = gather_parity(cone_parity(
+          st, global_extent, read_host, 2, seed=50 + rank, required=required,
+          rows=(host_runner.begin, host_runner.end)))
+    del np_in, np_out
+    pinned_in.close()
+    pinned_out.close()
+    host_runner.close()
+    runner = None
 
   # ---- release the headline arrays, then the other BASELINE configs ---------
   if world == 1:
     plan.close()
     del d_in, d_out
-  else:
+  elif runner is not None:
+    runner.close()
     del runner
   torch.cuda.empty_cache()
 

@@ -58,7 +58,8 @@ typedef enum soda_cuda_status {
   SODA_CUDA_BAD_ARGUMENT = 1,
   SODA_CUDA_CUDA_ERROR = 2,
   SODA_CUDA_UNSUPPORTED = 3,
-  SODA_CUDA_OUT_OF_MEMORY = 4
+  SODA_CUDA_OUT_OF_MEMORY = 4,
+  SODA_CUDA_COMM_ERROR = 5   /* NCCL or the exchange callback failed */
 } soda_cuda_status;
 
 typedef enum soda_cuda_dtype {
@@ -81,7 +82,10 @@ typedef struct soda_cuda_opts {
                           * SODA_CUDA_AUTOTUNE=0 in the environment, when that one-time
                           * synchronisation is unwanted (e.g. while capturing a CUDA graph) */
   int32_t reserved[5];   /* reserved[0]: chunks of the pipelined host path (copy/compute
-                          * overlap of soda_cuda_plan_run_host); 0 = auto, 1 = off */
+                          * overlap of soda_cuda_plan_run_host); 0 = auto, 1 = off
+                          * reserved[1]: soda_cuda_<app> / soda_cuda_run_host split the
+                          * grid over this many devices (0 .. n-1) when > 1
+                          * (sodac --cuda-gpus; see soda_cuda_multi_run_host) */
 } soda_cuda_opts;
 
 /* One pass = one HBM round trip = `time_block` fused iterations. */
@@ -179,6 +183,125 @@ SODA_CUDA_API int soda_cuda_run_pass(int32_t pass_index, const int32_t* extent,
  * soda_cuda_<app> does too and calls this function. */
 SODA_CUDA_API int soda_cuda_set_param(int32_t index, const void* values,
                                       const soda_cuda_opts* opts);
+
+/* ---- multi-GPU: one slab of a larger grid per device ------------------------
+ *
+ * The reference has no distributed path (its host drives one FPGA image,
+ * src/soda/codegen/frt/host.py:62-431); BASELINE.json's north star asks for
+ * grids split along the outermost dimension over the GPUs of one box with a
+ * halo exchange per time block.  A slab is one rank's share of the global
+ * grid: its own slices of the streamed (last) dimension plus ghost slices on
+ * both sides.  Passes run in exchange groups - k passes between two halo
+ * exchanges, each pass also storing the ghost slices the rest of its group
+ * still reads - and the last pass of a group is issued as three launches so
+ * that the exchange of the boundary slices overlaps the interior.
+ *
+ * Two transports move the halos: the library's own NCCL communicator
+ * (soda_cuda_slab_opts.nccl_id from soda_cuda_nccl_unique_id, distributed to
+ * all ranks by the caller; libnccl.so.2 is loaded at run time), or a callback
+ * (soda_cuda_slab_opts.exchange) for hosts that already have a communication
+ * layer (torch.distributed, MPI).  One process per GPU, or one process driving
+ * several devices with one slab each (soda_cuda_multi_run_host). */
+
+#define SODA_CUDA_NCCL_ID_BYTES 128
+
+typedef struct soda_cuda_slab soda_cuda_slab;   /* opaque */
+
+/* One transfer of a halo exchange: `bytes` bytes at `ptr` (device memory of
+ * this slab's device) to or from rank `peer`.  Transfers between two ranks are
+ * matched in order, like ncclSend / ncclRecv inside one group. */
+typedef struct soda_cuda_halo_op {
+  int32_t send;    /* 1: send to `peer`, 0: receive from `peer` */
+  int32_t peer;
+  void* ptr;
+  int64_t bytes;
+} soda_cuda_halo_op;
+
+/* Callback transport.  phase 0: start all `num_ops` transfers, ordered after
+ * the work already queued on `stream` (cudaStream_t); phase 1 (ops == NULL):
+ * make `stream` wait for the transfers started last.  Returns 0 on success. */
+typedef int (*soda_cuda_exchange_fn)(void* user, int32_t phase,
+                                     const soda_cuda_halo_op* ops, int32_t num_ops,
+                                     void* stream);
+
+typedef struct soda_cuda_slab_opts {
+  int32_t struct_size;
+  int32_t rank;
+  int32_t world;
+  int32_t device;          /* CUDA device ordinal; -1 = current device */
+  void* stream;            /* cudaStream_t of the passes; NULL = default stream */
+  int32_t segment;         /* as soda_cuda_opts.segment */
+  int32_t exchange_every;  /* passes per halo exchange; 0 = as many as keep the ghost
+                            * below 2.5 % of the slab; -1 = all (one exchange per run) */
+  int32_t no_overlap;      /* 1: exchange after the whole last pass of a group */
+  int32_t host_chunks;     /* chunks of soda_cuda_slab_run_host; 0 = auto */
+  soda_cuda_exchange_fn exchange;   /* NULL: the native NCCL transport */
+  void* exchange_user;
+  const void* nccl_id;     /* SODA_CUDA_NCCL_ID_BYTES bytes, identical on all ranks
+                            * (native transport, world > 1) */
+  int32_t reserved[8];     /* reserved[0] = 1: dry run - bounds, ghost depths and exchange
+                            * groups only (soda_cuda_slab_get_info); nothing is allocated */
+} soda_cuda_slab_opts;
+
+typedef struct soda_cuda_slab_info {
+  int32_t begin, end;              /* global slices this rank owns */
+  int32_t local_begin, local_end;  /* global slices its arrays cover (own + ghosts) */
+  int32_t ghost_lo, ghost_hi;      /* ghost depth a group needs before its first pass */
+  int32_t local_extent[SODA_CUDA_MAX_DIM];
+  int64_t pitch[2];                /* elements between rows / planes of every array */
+  int32_t num_groups;
+  int32_t group_passes[16];        /* passes of the first 16 groups */
+} soda_cuda_slab_info;
+
+/* Rank 0 calls this and hands the bytes to every rank (native transport). */
+SODA_CUDA_API int soda_cuda_nccl_unique_id(void* id_bytes);
+
+SODA_CUDA_API int soda_cuda_slab_create(const int32_t* global_extent,
+                                        const soda_cuda_slab_opts* opts,
+                                        soda_cuda_slab** slab);
+SODA_CUDA_API int soda_cuda_slab_destroy(soda_cuda_slab* slab);
+SODA_CUDA_API int soda_cuda_slab_get_info(const soda_cuda_slab* slab,
+                                          soda_cuda_slab_info* info);
+
+/* Device addresses of the slab's local arrays (num_inputs + num_outputs
+ * pointers; shape local_extent, pitches `pitch`).  The caller fills its own
+ * slices [begin - local_begin, end - local_begin) of the inputs; ghost slices
+ * are refreshed by soda_cuda_slab_run. */
+SODA_CUDA_API int soda_cuda_slab_buffers(soda_cuda_slab* slab, void** d_in, void** d_out);
+
+/* All `iterate` iterations, device-resident: inputs -> outputs.  Queued on the
+ * slab's stream; returns after everything (passes and exchanges) is queued. */
+SODA_CUDA_API int soda_cuda_slab_run(soda_cuda_slab* slab);
+
+/* One halo exchange of the input arrays, `depth_lo` / `depth_hi` ghost slices
+ * (benchmarks time this on its own). */
+SODA_CUDA_API int soda_cuda_slab_exchange_inputs(soda_cuda_slab* slab, int32_t depth_lo,
+                                                 int32_t depth_hi);
+
+/* Host arrays holding this rank's own slices (extent = the global extent with
+ * the last dimension replaced by end - begin) in, the same slices of the
+ * outputs out: chunked H2D / passes / D2H pipeline per rank, the ghost slices
+ * of the inputs arrive from the neighbouring ranks' uploads while the interior
+ * chunks compute.  Needs a slab created with exchange_every = -1.  Blocks. */
+SODA_CUDA_API int soda_cuda_slab_run_host(soda_cuda_slab* slab,
+                            const void* const* in_ptrs, const int32_t* const* in_strides,
+                            void* const* out_ptrs, const int32_t* const* out_strides);
+
+/* One process, `num_devices` GPUs (sodac --cuda-gpus N): the whole grid in host
+ * arrays, as soda_cuda_run_host; every device uploads its slab and the ghost
+ * slices it needs straight from the host arrays, so the devices never talk to
+ * each other.  `devices` may be NULL (0 .. num_devices-1).  Blocks. */
+SODA_CUDA_API int soda_cuda_multi_run_host(const void* const* in_ptrs,
+                             const int32_t* const* in_strides,
+                             void* const* out_ptrs, const int32_t* const* out_strides,
+                             const int32_t* extent, const int32_t* devices,
+                             int32_t num_devices, const soda_cuda_opts* opts);
+
+/* Page-locked host memory on the NUMA node of `device` (first-touch under an
+ * mbind policy when the box has several nodes, then cudaHostRegister), for the
+ * staging arrays of the host entry points. */
+SODA_CUDA_API int soda_cuda_host_alloc(void** ptr, int64_t bytes, int32_t device);
+SODA_CUDA_API int soda_cuda_host_free(void* ptr, int64_t bytes);
 
 /* Number of kernel launches issued by this library since it was loaded. */
 SODA_CUDA_API int64_t soda_cuda_launch_count(void);

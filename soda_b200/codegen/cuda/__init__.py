@@ -64,6 +64,11 @@ def add_arguments(parser) -> None:
                       dest='cuda_no_pack',
                       help='do not use packed fp32 pairs (FADD2/FMUL2) for '
                       'float add/mul programs')
+  parser.add_argument('--cuda-gpus', type=int, dest='cuda_gpus', metavar='N',
+                      help='the program-named entry point splits the grid '
+                      'along the outermost dimension over N devices of the '
+                      'calling process (soda_cuda_multi_run_host); a caller '
+                      'can still override it per call')
   parser.add_argument('--cuda-fast-fp', action='store_true',
                       dest='cuda_fast_fp',
                       help='allow FMA contraction (default: off, results are '
@@ -80,6 +85,7 @@ def options_from_args(args: Optional[argparse.Namespace]) -> Dict:
       'stages': get('cuda_stages'),
       'cy': get('cuda_patch_rows'),
       'min_blocks': get('cuda_min_blocks'),
+      'gpus': get('cuda_gpus'),
       'no_pipeline': bool(get('cuda_no_pipeline')),
       'fast_fp': bool(get('cuda_fast_fp')),
       'no_pack': bool(get('cuda_no_pack')),

@@ -16,6 +16,7 @@ kernels").  The reference's counterpart is the HLS kernel printer
 (reference: src/soda/codegen/xilinx/hls_kernel.py:338-971), which does print
 free-form modules.
 """
+import logging
 import math
 from typing import Dict, List, Optional, Sequence
 
@@ -309,6 +310,19 @@ def emit_program(stencil,
   # integer widths C++ does not have become containers + explicit wraps
   stencil = widths.lower(stencil)
   dim = stencil.dim
+  for what, stmts in (('inputs', stencil.input_stmts),
+                      ('outputs', stencil.output_stmts),
+                      ('params', stencil.param_stmts)):
+    if len(stmts) > 8:  # SODA_CUDA_MAX_TENSORS: fixed-size tables of the ABI
+      raise util.SemanticError('the CUDA backend supports at most 8 %s, the '
+                               'program has %d' % (what, len(stmts)))
+  if getattr(stencil, 'preserve_border', False):
+    # "Reserved" in the reference (src/soda/core.py:30); its FRT host - the path
+    # this backend replaces - ignores it too (only the legacy Xilinx host reads
+    # it, src/soda/codegen/xilinx/host.py:855).  Say so instead of silence.
+    logging.getLogger(__name__).warning(
+        'border: preserve has no effect in the CUDA backend: cells outside '
+        'the valid box keep the caller\'s bytes (as with border: ignore)')
   time_block = planner.choose_time_block(stencil, time_block, options)
   schedule = planner.pass_schedule(stencil.iterate, time_block)
   variants = sorted(set(schedule), reverse=True)
@@ -468,6 +482,18 @@ def emit_program(stencil,
                ', '.join('var_%s_ptr' % s.name for s in stencil.output_stmts))
   lines.append('  const int32_t* out_strides[] = {%s};' % ', '.join(
       'var_%s_stride' % s.name for s in stencil.output_stmts))
+  gpus = int(options.get('gpus') or 0)
+  if gpus > 1:
+    # sodac --cuda-gpus N: the default of this library, unless the caller's
+    # opts name a device count themselves
+    lines.append('  soda_cuda_opts soda_opts;')
+    lines.append('  memset(&soda_opts, 0, sizeof(soda_opts));')
+    lines.append('  soda_opts.device = -1;')
+    lines.append('  if (opts != nullptr) soda_opts = *opts;')
+    lines.append('  soda_opts.struct_size = sizeof(soda_opts);')
+    lines.append('  if (soda_opts.reserved[1] == 0) soda_opts.reserved[1] = %d;'
+                 % gpus)
+    lines.append('  opts = &soda_opts;')
   lines.append('  return soda_cuda_run_host(in_ptrs, in_strides, out_ptrs, '
                'out_strides, var_%s_extent, opts);' % first)
   lines.append('}')

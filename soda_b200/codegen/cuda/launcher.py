@@ -32,6 +32,18 @@ EXPORTED_SYMBOLS = (
     'soda_cuda_run_pass',
     'soda_cuda_launch_count',
     'soda_cuda_set_param',
+    # multi-GPU slabs
+    'soda_cuda_nccl_unique_id',
+    'soda_cuda_slab_create',
+    'soda_cuda_slab_destroy',
+    'soda_cuda_slab_get_info',
+    'soda_cuda_slab_buffers',
+    'soda_cuda_slab_run',
+    'soda_cuda_slab_exchange_inputs',
+    'soda_cuda_slab_run_host',
+    'soda_cuda_multi_run_host',
+    'soda_cuda_host_alloc',
+    'soda_cuda_host_free',
 )
 
 
@@ -90,15 +102,17 @@ class ProgramInfo(ctypes.Structure):
 
 
 def make_opts(device: int = -1, stream: int = 0, segment: int = 0,
-              host_chunks: int = 0) -> Opts:
+              host_chunks: int = 0, gpus: int = 0) -> Opts:
   """``host_chunks``: chunk count of the copy/compute pipeline used for host
-  arrays (0 = automatic, 1 = no pipelining)."""
+  arrays (0 = automatic, 1 = no pipelining).  ``gpus`` > 1: host-array calls
+  split the grid over that many devices of this process."""
   opts = Opts()
   opts.struct_size = ctypes.sizeof(Opts)
   opts.device = device
   opts.stream = stream or None
   opts.segment = segment
   opts.reserved[0] = host_chunks
+  opts.reserved[1] = gpus
   return opts
 
 
@@ -300,6 +314,35 @@ class CudaProgram:
         self.lib.soda_cuda_run_pass(pass_index, c_extent, in_ptrs, in_p,
                                     out_ptrs, out_p, lo, hi,
                                     ctypes.byref(opts) if opts else None))
+
+
+class HostBuffer:
+  """Page-locked host array on the NUMA node of a device
+  (``soda_cuda_host_alloc``): the staging memory of the host entry points."""
+
+  def __init__(self, program: 'CudaProgram', shape: Sequence[int], dtype,
+               device: int = -1):
+    self.program = program
+    self.dtype = np.dtype(dtype)
+    self.nbytes = int(np.prod(shape)) * self.dtype.itemsize
+    self.ptr = ctypes.c_void_p()
+    program._check(program.lib.soda_cuda_host_alloc(
+        ctypes.byref(self.ptr), ctypes.c_int64(self.nbytes), device))
+    raw = (ctypes.c_char * self.nbytes).from_address(self.ptr.value)
+    self.array = np.frombuffer(raw, dtype=self.dtype).reshape(tuple(shape))
+
+  def close(self) -> None:
+    if self.ptr:
+      self.array = None
+      self.program.lib.soda_cuda_host_free(self.ptr,
+                                           ctypes.c_int64(self.nbytes))
+      self.ptr = ctypes.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
 
 
 class Plan:

@@ -246,22 +246,42 @@ inline int choose_segment(int slices, int ctas_per_slice_set, int warmup,
   return ceil_div(slices, static_cast<int>(segments));
 }
 
+// The dynamic shared-memory attribute and the occupancy of a kernel are per
+// device: one process may drive several (soda_cuda_opts.device, the slab and
+// multi-device entry points).  Set / queried once per (kernel, device).
+constexpr int kMaxDevices = 64;
+template <class Kernel>
+int kernel_setup(Kernel kernel, int threads, int smem_bytes, int* ctas_per_sm) {
+  static std::mutex mutex;
+  static bool done[kMaxDevices] = {};
+  static int occupancy[kMaxDevices] = {};
+  int device = 0;
+  SODA_CUDA_CHECK(cudaGetDevice(&device));
+  if (device < 0 || device >= kMaxDevices)
+    return fail(SODA_CUDA_UNSUPPORTED, "device ordinal out of range");
+  std::lock_guard<std::mutex> lock(mutex);
+  if (!done[device]) {
+    SODA_CUDA_CHECK(cudaFuncSetAttribute(
+        kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    int blocks = 1;
+    SODA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &blocks, kernel, threads, smem_bytes));
+    occupancy[device] = blocks < 1 ? 1 : blocks;
+    done[device] = true;
+  }
+  *ctas_per_sm = occupancy[device];
+  return SODA_CUDA_OK;
+}
+
 template <class Prog>
 int launch_pass_2d(const PassArgs& a) {
   using S = Smem2D<Prog>;
   auto kernel = soda_stream2d_kernel<Prog>;
-  static std::once_flag once;
-  static cudaError_t attr_status = cudaSuccess;
-  static int ctas_per_sm = 1;
-  std::call_once(once, [&] {
-    attr_status = cudaFuncSetAttribute(
-        kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes);
-    if (attr_status == cudaSuccess)
-      attr_status = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &ctas_per_sm, kernel, Prog::kWarps * 32, S::kBytes);
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-  });
-  SODA_CUDA_CHECK(attr_status);
+  int ctas_per_sm = 1;
+  {
+    int status = kernel_setup(kernel, Prog::kWarps * 32, S::kBytes, &ctas_per_sm);
+    if (status != SODA_CUDA_OK) return status;
+  }
 
   Params2D<Prog> p;
   memset(&p, 0, sizeof(p));
@@ -304,18 +324,11 @@ template <class Prog>
 int launch_pass_3d(const PassArgs& a) {
   using S = Smem3D<Prog>;
   auto kernel = soda_stream3d_kernel<Prog>;
-  static std::once_flag once;
-  static cudaError_t attr_status = cudaSuccess;
-  static int ctas_per_sm = 1;
-  std::call_once(once, [&] {
-    attr_status = cudaFuncSetAttribute(
-        kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes);
-    if (attr_status == cudaSuccess)
-      attr_status = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &ctas_per_sm, kernel, Prog::kWarps * 32, S::kBytes);
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-  });
-  SODA_CUDA_CHECK(attr_status);
+  int ctas_per_sm = 1;
+  {
+    int status = kernel_setup(kernel, Prog::kWarps * 32, S::kBytes, &ctas_per_sm);
+    if (status != SODA_CUDA_OK) return status;
+  }
 
   Params3D<Prog> p;
   memset(&p, 0, sizeof(p));
@@ -473,9 +486,17 @@ inline int launch_tuned(const ProgramDesc& prog, int variant, PassArgs a) {
   const long long counted = launch_counter().load();
   int status = impl.launch(a);  // untimed: module load, attributes, cold caches
   if (status != SODA_CUDA_OK) return status;
-  cudaEvent_t start, stop;
-  SODA_CUDA_CHECK(cudaEventCreate(&start));
-  SODA_CUDA_CHECK(cudaEventCreate(&stop));
+  // destroyed on every exit path
+  struct Events {
+    cudaEvent_t start = nullptr, stop = nullptr;
+    ~Events() {
+      if (start) cudaEventDestroy(start);
+      if (stop) cudaEventDestroy(stop);
+    }
+  } events;
+  SODA_CUDA_CHECK(cudaEventCreate(&events.start));
+  SODA_CUDA_CHECK(cudaEventCreate(&events.stop));
+  cudaEvent_t start = events.start, stop = events.stop;
   auto measure = [&](int segment, float* ms) -> int {
     PassArgs trial = a;
     trial.segment = segment;
@@ -527,8 +548,6 @@ inline int launch_tuned(const ProgramDesc& prog, int variant, PassArgs a) {
       break;
     }
   }
-  cudaEventDestroy(start);
-  cudaEventDestroy(stop);
   launch_counter().store(counted + 1);  // the tuning launches repeat one pass
   if (status != SODA_CUDA_OK) return status;
   cache[key] = best_segment;
@@ -546,11 +565,11 @@ static const soda::rt::ProgramDesc& soda_program();
 
 // ---- plan ---------------------------------------------------------------------
 struct soda_cuda_plan {
-  int extent[soda::rt::kMaxD];
+  int extent[soda::rt::kMaxD];  // extent of the plan's arrays (a slab: local)
   int device;
   cudaStream_t stream;
   int segment;
-  // device staging for host-array calls
+  // device staging for host-array calls (a slab: its local arrays)
   void* d_in[soda::rt::kMaxT];
   void* d_out[soda::rt::kMaxT];
   // ping-pong scratch between passes, per output
@@ -559,6 +578,13 @@ struct soda_cuda_plan {
   int host_chunks;     // requested chunk count of the pipelined host path, 0 = auto
   cudaStream_t copy_in_stream;   // H2D of chunk k+1 overlaps compute of chunk k
   cudaStream_t copy_out_stream;  // ... and D2H of chunk k-1
+  // Slices of the streamed dimension, in the plan's own coordinates, in which
+  // the final output is valid.  A stand-alone plan covers the whole grid:
+  // [final_lo, extent - final_hi).  A slab's arrays are a window of a larger
+  // grid, so the range comes from the global grid (it may start below 0 or
+  // end beyond the local extent: only the global border clips).
+  int s_valid_lo[soda::rt::kMaxT];
+  int s_valid_hi[soda::rt::kMaxT];
 };
 
 namespace soda {
@@ -576,13 +602,32 @@ inline int plan_alloc(soda_cuda_plan* plan, void** ptr, int elem_bytes) {
   return SODA_CUDA_OK;
 }
 
-inline void default_boxes(const ProgramDesc& prog, const int* extent,
+// Store boxes of one pass over the plan's arrays: everything for an
+// intermediate pass, the program's final valid box for the last one.
+inline void default_boxes(const ProgramDesc& prog, const soda_cuda_plan* plan,
                           bool final_pass, int (*lo)[kMaxD], int (*hi)[kMaxD]) {
+  const int s_dim = prog.info.dim - 1;
   for (int o = 0; o < prog.info.num_outputs; ++o) {
     for (int d = 0; d < prog.info.dim; ++d) {
       lo[o][d] = final_pass ? prog.info.final_lo[o][d] : 0;
-      hi[o][d] = extent[d] - (final_pass ? prog.info.final_hi[o][d] : 0);
+      hi[o][d] = plan->extent[d] - (final_pass ? prog.info.final_hi[o][d] : 0);
     }
+    if (final_pass) {
+      lo[o][s_dim] = std::max(0, plan->s_valid_lo[o]);
+      hi[o][s_dim] = std::min(plan->extent[s_dim], plan->s_valid_hi[o]);
+    }
+  }
+}
+
+// What all passes together depend on along the streamed dimension.
+inline void total_reach(const ProgramDesc& prog, int* reach_lo, int* reach_hi) {
+  const int s_dim = prog.info.dim - 1;
+  *reach_lo = *reach_hi = 0;
+  for (int pass = 0; pass < prog.info.num_passes; ++pass) {
+    const soda_cuda_pass_info& info = prog.impls[prog.schedule[pass]].info;
+    // one-sided windows: a pass never reaches less than its own slice
+    *reach_lo += std::max(0, -info.reach_lo[s_dim]);
+    *reach_hi += std::max(0, info.reach_hi[s_dim]);
   }
 }
 
@@ -602,12 +647,7 @@ inline int run_passes_window(soda_cuda_plan* plan, const void* const* d_in,
   const int num_passes = prog.info.num_passes;
   const int n_in = prog.info.num_inputs, n_out = prog.info.num_outputs;
   int reach_lo = 0, reach_hi = 0;
-  for (int pass = 0; pass < num_passes; ++pass) {
-    const soda_cuda_pass_info& info = prog.impls[prog.schedule[pass]].info;
-    // one-sided windows: a pass never reaches less than its own slice
-    reach_lo += std::max(0, -info.reach_lo[s_dim]);
-    reach_hi += std::max(0, info.reach_hi[s_dim]);
-  }
+  total_reach(prog, &reach_lo, &reach_hi);
   const int total = plan->extent[s_dim];
   const int view_lo = s_begin - reach_lo > 0 ? s_begin - reach_lo : 0;
   const int view_hi = s_end + reach_hi < total ? s_end + reach_hi : total;
@@ -653,7 +693,7 @@ inline int run_passes_window(soda_cuda_plan* plan, const void* const* d_in,
         a.out_pitch[o][1] = plan->pitch[1];
       }
     }
-    default_boxes(prog, plan->extent, last, a.box_lo, a.box_hi);
+    default_boxes(prog, plan, last, a.box_lo, a.box_hi);
     for (int o = 0; o < n_out; ++o) {
       if (last) {
         int lo = a.box_lo[o][s_dim] > s_begin ? a.box_lo[o][s_dim] : s_begin;
@@ -694,11 +734,15 @@ inline int check_strides(const int32_t* stride, const int* extent, int dim,
   return SODA_CUDA_OK;
 }
 
-// Copies the box [lo, hi) between a strided host array and a plan buffer.
+// Copies the box [lo, hi) (plan coordinates) between a strided host array and
+// a plan buffer.  Slice s of the plan is slice s + host_shift of the host
+// array (0 for a stand-alone plan; a slab's arrays start elsewhere than the
+// caller's).
 inline int copy_box(const soda_cuda_plan* plan, cudaStream_t stream, int dim,
                     void* device,
                     void* host, const int32_t* host_stride, int elem_bytes,
-                    const int* lo, const int* hi, bool to_device) {
+                    const int* lo, const int* hi, bool to_device,
+                    int host_shift = 0) {
   long long hs[kMaxD] = {1, plan->extent[0],
                          static_cast<long long>(plan->extent[0]) * plan->extent[1]};
   if (host_stride != nullptr)
@@ -707,7 +751,8 @@ inline int copy_box(const soda_cuda_plan* plan, cudaStream_t stream, int dim,
   if (dim == 2) {
     char* d_ptr = static_cast<char*>(device) +
                   (plan->pitch[0] * lo[1] + lo[0]) * elem_bytes;
-    char* h_ptr = static_cast<char*>(host) + (hs[1] * lo[1] + lo[0]) * elem_bytes;
+    char* h_ptr = static_cast<char*>(host) +
+                  (hs[1] * (lo[1] + host_shift) + lo[0]) * elem_bytes;
     const size_t rows = hi[1] - lo[1];
     if (to_device) {
       SODA_CUDA_CHECK(cudaMemcpy2DAsync(d_ptr, plan->pitch[0] * elem_bytes, h_ptr,
@@ -730,16 +775,231 @@ inline int copy_box(const soda_cuda_plan* plan, cudaStream_t stream, int dim,
       plan->pitch[1] / plan->pitch[0]);
   cudaPitchedPtr h_pitched = make_cudaPitchedPtr(
       host, hs[1] * elem_bytes, hs[1] * elem_bytes, hs[2] / hs[1]);
-  cudaPos pos = make_cudaPos(static_cast<size_t>(lo[0]) * elem_bytes, lo[1], lo[2]);
+  cudaPos d_pos = make_cudaPos(static_cast<size_t>(lo[0]) * elem_bytes, lo[1], lo[2]);
+  cudaPos h_pos = make_cudaPos(static_cast<size_t>(lo[0]) * elem_bytes, lo[1],
+                               lo[2] + host_shift);
   parms.srcPtr = to_device ? h_pitched : d_pitched;
   parms.dstPtr = to_device ? d_pitched : h_pitched;
-  parms.srcPos = pos;
-  parms.dstPos = pos;
+  parms.srcPos = to_device ? h_pos : d_pos;
+  parms.dstPos = to_device ? d_pos : h_pos;
   parms.extent = make_cudaExtent(width, hi[1] - lo[1], hi[2] - lo[2]);
   parms.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
   SODA_CUDA_CHECK(cudaMemcpy3DAsync(&parms, stream));
   return SODA_CUDA_OK;
 }
+
+// ---- chunked host pipeline -------------------------------------------------------
+// Host arrays in, host arrays out, through the plan's device arrays: the
+// slices [own_lo, own_hi) of the plan are produced in chunks along the streamed
+// dimension.  chunk k: H2D (copy-in stream) -> all passes on its window (plan
+// stream) -> D2H of its valid interior (copy-out stream); the copies of
+// neighbouring chunks overlap the compute.  Chunks overlap by the total reach
+// of all passes, so the price is (reach / chunk) redundant compute.
+//
+// A stand-alone plan owns every slice and the host arrays hold all of them.
+// A slab (soda_slab.cuh) owns the middle of its arrays: the host holds
+// [host_lo, host_hi) (its own slices, or - one process driving several devices
+// from one global host array - the ghost slices too), and ghost slices the
+// host does not hold arrive from the neighbouring ranks: `after_edges` is
+// called once the slices next to the slab boundaries are queued for upload
+// (it starts the exchange, ordered after the copy-in stream), `before_edge`
+// before the first chunk that reads ghost slices is computed (it makes the
+// plan stream wait for the exchange).
+struct HostPipeline {
+  soda_cuda_plan* plan = nullptr;
+  const void* const* in_ptrs = nullptr;
+  const int32_t* const* in_strides = nullptr;
+  void* const* out_ptrs = nullptr;
+  const int32_t* const* out_strides = nullptr;
+  int own_lo = 0, own_hi = 0;    // slices to produce (plan coordinates)
+  int host_lo = 0, host_hi = 0;  // slices the host arrays hold
+  int host_shift = 0;            // plan slice s is host slice s + host_shift
+  bool ghosts_from_peers = false;
+  int (*after_edges)(void* user, cudaStream_t copy_in) = nullptr;
+  int (*before_edge)(void* user, cudaStream_t compute) = nullptr;
+  void* user = nullptr;
+  // state between issue() and finish()
+  std::vector<cudaEvent_t> events;
+  int result = SODA_CUDA_OK;
+
+  int new_event(cudaEvent_t* event) {
+    SODA_CUDA_CHECK(cudaEventCreateWithFlags(event, cudaEventDisableTiming));
+    events.push_back(*event);
+    return SODA_CUDA_OK;
+  }
+
+  static int choose_chunks(const ProgramDesc& prog, const soda_cuda_plan* plan,
+                           int slices) {
+    int reach_lo = 0, reach_hi = 0;
+    total_reach(prog, &reach_lo, &reach_hi);
+    const int reach = reach_lo + reach_hi;
+    long long bytes = 0;
+    const long long slice_cells =
+        prog.info.dim == 2 ? plan->pitch[0] : plan->pitch[1];
+    for (int i = 0; i < prog.info.num_inputs; ++i)
+      bytes += slice_cells * slices * prog.in_elem_bytes[i];
+    int chunks = plan->host_chunks;
+    if (chunks <= 0) {
+      chunks = 1;
+      if (bytes >= (32LL << 20)) {
+        // chunks of at least 8x the reach: at most 12.5 % redundant compute at
+        // the seams, and windows tall enough to fill the GPU (32 chunks of the
+        // 16384^2 x 64 workload were measured slower than 16: 30.9 vs 25.8 ms)
+        chunks = slices / (8 * (reach > 0 ? reach : 1));
+        if (chunks > 16) chunks = 16;
+        if (chunks < 1) chunks = 1;
+      }
+    }
+    if (chunks > slices) chunks = slices;
+    return chunks < 1 ? 1 : chunks;
+  }
+
+  // Queues everything; nothing here waits for the device (pinned host memory).
+  int issue() {
+    const ProgramDesc& prog = soda_program();
+    const int dim = prog.info.dim, s_dim = dim - 1;
+    const int n_in = prog.info.num_inputs, n_out = prog.info.num_outputs;
+    long long pitches[kMaxT][2];
+    for (int i = 0; i < kMaxT; ++i) {
+      pitches[i][0] = plan->pitch[0];
+      pitches[i][1] = plan->pitch[1];
+    }
+    const int slices = own_hi - own_lo;
+    if (slices <= 0) return SODA_CUDA_OK;
+    const int chunks = choose_chunks(prog, plan, slices);
+    int reach_lo = 0, reach_hi = 0;
+    total_reach(prog, &reach_lo, &reach_hi);
+
+    if (plan->copy_in_stream == nullptr) {
+      SODA_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->copy_in_stream,
+                                                cudaStreamNonBlocking));
+      SODA_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->copy_out_stream,
+                                                cudaStreamNonBlocking));
+    }
+    auto upload = [&](int lo_s, int hi_s) -> int {
+      if (hi_s <= lo_s) return SODA_CUDA_OK;
+      int c_lo[kMaxD] = {0, 0, 0}, c_hi[kMaxD];
+      for (int d = 0; d < dim; ++d) c_hi[d] = plan->extent[d];
+      c_lo[s_dim] = lo_s;
+      c_hi[s_dim] = hi_s;
+      for (int i = 0; i < n_in; ++i) {
+        int status = copy_box(plan, plan->copy_in_stream, dim, plan->d_in[i],
+                              const_cast<void*>(in_ptrs[i]),
+                              in_strides ? in_strides[i] : nullptr,
+                              prog.in_elem_bytes[i], c_lo, c_hi, true, host_shift);
+        if (status != SODA_CUDA_OK) return status;
+      }
+      return SODA_CUDA_OK;
+    };
+
+    // the copy-in stream must not run ahead of work already queued on the plan
+    // stream that still reads the staging buffers (a previous call)
+    cudaEvent_t start_event;
+    int status = new_event(&start_event);
+    if (status != SODA_CUDA_OK) return status;
+    SODA_CUDA_CHECK(cudaEventRecord(start_event, plan->stream));
+    SODA_CUDA_CHECK(cudaStreamWaitEvent(plan->copy_in_stream, start_event, 0));
+
+    const bool peers = ghosts_from_peers && after_edges != nullptr;
+    if (peers) {
+      // what the neighbours need from this rank goes first (a few slices,
+      // uploaded again with their chunk), then the exchange runs beside the
+      // remaining uploads
+      status = upload(own_lo, std::min(own_hi, own_lo + reach_hi));
+      if (status == SODA_CUDA_OK)
+        status = upload(std::max(own_lo, own_hi - reach_lo), own_hi);
+      if (status == SODA_CUDA_OK) status = after_edges(user, plan->copy_in_stream);
+      if (status != SODA_CUDA_OK) return status;
+    }
+
+    // upload pieces: the chunk bounds, stretched to what the host holds
+    std::vector<int> bound(chunks + 1), piece(chunks + 1);
+    for (int k = 0; k <= chunks; ++k)
+      bound[k] = own_lo + static_cast<int>(static_cast<long long>(slices) * k / chunks);
+    piece = bound;
+    piece[0] = host_lo;
+    piece[chunks] = host_hi;
+    std::vector<cudaEvent_t> copied(chunks), computed(chunks);
+    for (int k = 0; k < chunks; ++k) {
+      status = new_event(&copied[k]);
+      if (status == SODA_CUDA_OK) status = new_event(&computed[k]);
+      if (status != SODA_CUDA_OK) return status;
+    }
+    for (int k = 0; k < chunks; ++k) {
+      status = upload(piece[k], piece[k + 1]);
+      if (status != SODA_CUDA_OK) return status;
+      SODA_CUDA_CHECK(cudaEventRecord(copied[k], plan->copy_in_stream));
+    }
+
+    // compute order: chunks that read ghost slices from the neighbours last
+    std::vector<int> order;
+    for (int k = 0; k < chunks; ++k) {
+      const bool edge = peers && (bound[k] - reach_lo < host_lo ||
+                                  bound[k + 1] + reach_hi > host_hi);
+      if (!edge) order.push_back(k);
+    }
+    const size_t interior = order.size();
+    for (int k = 0; k < chunks; ++k)
+      if (std::find(order.begin(), order.end(), k) == order.end())
+        order.push_back(k);
+
+    int lo[kMaxT][kMaxD], hi[kMaxT][kMaxD];
+    default_boxes(prog, plan, true, lo, hi);
+    bool waited_for_peers = false;
+    for (size_t n = 0; n < order.size(); ++n) {
+      const int k = order[n];
+      if (n >= interior && !waited_for_peers && before_edge != nullptr) {
+        status = before_edge(user, plan->stream);
+        if (status != SODA_CUDA_OK) return status;
+        waited_for_peers = true;
+      }
+      // the window of chunk k ends at bound[k+1] + reach_hi: wait for the last
+      // piece it touches (uploads are issued in order on one stream)
+      int last_needed = k;
+      while (last_needed + 1 < chunks &&
+             piece[last_needed + 1] < bound[k + 1] + reach_hi)
+        ++last_needed;
+      SODA_CUDA_CHECK(cudaStreamWaitEvent(plan->stream, copied[last_needed], 0));
+      status = run_passes_window(plan, plan->d_in, pitches, plan->d_out, pitches,
+                                 bound[k], bound[k + 1]);
+      if (status != SODA_CUDA_OK) return status;
+      SODA_CUDA_CHECK(cudaEventRecord(computed[k], plan->stream));
+      SODA_CUDA_CHECK(cudaStreamWaitEvent(plan->copy_out_stream, computed[k], 0));
+      for (int o = 0; o < n_out; ++o) {
+        int o_lo[kMaxD], o_hi[kMaxD];
+        bool empty = false;
+        for (int d = 0; d < dim; ++d) {
+          o_lo[d] = lo[o][d];
+          o_hi[d] = hi[o][d];
+        }
+        if (o_lo[s_dim] < bound[k]) o_lo[s_dim] = bound[k];
+        if (o_hi[s_dim] > bound[k + 1]) o_hi[s_dim] = bound[k + 1];
+        for (int d = 0; d < dim; ++d) empty = empty || o_hi[d] <= o_lo[d];
+        if (empty) continue;
+        status = copy_box(plan, plan->copy_out_stream, dim, plan->d_out[o],
+                          out_ptrs[o], out_strides ? out_strides[o] : nullptr,
+                          prog.out_elem_bytes[o], o_lo, o_hi, false, host_shift);
+        if (status != SODA_CUDA_OK) return status;
+      }
+    }
+    return SODA_CUDA_OK;
+  }
+
+  // Waits for everything issue() queued and releases its events.
+  int finish(int issue_status) {
+    cudaError_t sync_in = cudaSuccess, sync_out = cudaSuccess;
+    if (plan->copy_in_stream) sync_in = cudaStreamSynchronize(plan->copy_in_stream);
+    cudaError_t sync_compute = cudaStreamSynchronize(plan->stream);
+    if (plan->copy_out_stream) sync_out = cudaStreamSynchronize(plan->copy_out_stream);
+    for (cudaEvent_t event : events) cudaEventDestroy(event);
+    events.clear();
+    if (issue_status != SODA_CUDA_OK) return issue_status;
+    SODA_CUDA_CHECK(sync_in);
+    SODA_CUDA_CHECK(sync_compute);
+    SODA_CUDA_CHECK(sync_out);
+    return SODA_CUDA_OK;
+  }
+};
 
 struct DeviceGuard {
   int previous = -1;
@@ -837,6 +1097,11 @@ int soda_cuda_plan_create(const int32_t* extent, const soda_cuda_opts* opts,
   const long long row_align = 128;
   plan->pitch[0] = (extent[0] + row_align - 1) / row_align * row_align;
   plan->pitch[1] = prog.info.dim == 3 ? plan->pitch[0] * extent[1] : 0;
+  for (int o = 0; o < prog.info.num_outputs; ++o) {
+    const int s_dim = prog.info.dim - 1;
+    plan->s_valid_lo[o] = prog.info.final_lo[o][s_dim];
+    plan->s_valid_hi[o] = extent[s_dim] - prog.info.final_hi[o][s_dim];
+  }
   *out = plan;
   return SODA_CUDA_OK;
 }
@@ -883,6 +1148,34 @@ int soda_cuda_plan_run_device(soda_cuda_plan* plan, const void* const* d_in,
   return run_passes(plan, d_in, ip, d_out, op);
 }
 
+// Checks the caller's arrays and allocates the plan's staging buffers.
+static int soda_plan_prepare_host(soda_cuda_plan* plan, const void* const* in_ptrs,
+                                  const int32_t* const* in_strides,
+                                  void* const* out_ptrs,
+                                  const int32_t* const* out_strides,
+                                  const int* host_extent) {
+  using namespace soda::rt;
+  const ProgramDesc& prog = soda_program();
+  const int dim = prog.info.dim;
+  for (int i = 0; i < prog.info.num_inputs; ++i) {
+    if (in_ptrs[i] == nullptr) return fail(SODA_CUDA_BAD_ARGUMENT, "NULL input");
+    const int32_t* stride = in_strides ? in_strides[i] : nullptr;
+    int status = check_strides(stride, host_extent, dim, prog.info.input_names[i]);
+    if (status != SODA_CUDA_OK) return status;
+    status = plan_alloc(plan, &plan->d_in[i], prog.in_elem_bytes[i]);
+    if (status != SODA_CUDA_OK) return status;
+  }
+  for (int o = 0; o < prog.info.num_outputs; ++o) {
+    if (out_ptrs[o] == nullptr) return fail(SODA_CUDA_BAD_ARGUMENT, "NULL output");
+    const int32_t* stride = out_strides ? out_strides[o] : nullptr;
+    int status = check_strides(stride, host_extent, dim, prog.info.output_names[o]);
+    if (status != SODA_CUDA_OK) return status;
+    status = plan_alloc(plan, &plan->d_out[o], prog.out_elem_bytes[o]);
+    if (status != SODA_CUDA_OK) return status;
+  }
+  return SODA_CUDA_OK;
+}
+
 int soda_cuda_plan_run_host(soda_cuda_plan* plan, const void* const* in_ptrs,
                             const int32_t* const* in_strides,
                             void* const* out_ptrs,
@@ -895,6 +1188,9 @@ int soda_cuda_plan_run_host(soda_cuda_plan* plan, const void* const* in_ptrs,
   DeviceGuard guard;
   int status = guard.enter(plan->device);
   if (status != SODA_CUDA_OK) return status;
+  status = soda_plan_prepare_host(plan, in_ptrs, in_strides, out_ptrs, out_strides,
+                                  plan->extent);
+  if (status != SODA_CUDA_OK) return status;
 
   const int zero[kMaxD] = {0, 0, 0};
   long long pitches[kMaxT][2];
@@ -902,54 +1198,10 @@ int soda_cuda_plan_run_host(soda_cuda_plan* plan, const void* const* in_ptrs,
     pitches[i][0] = plan->pitch[0];
     pitches[i][1] = plan->pitch[1];
   }
-  for (int i = 0; i < prog.info.num_inputs; ++i) {
-    if (in_ptrs[i] == nullptr) return fail(SODA_CUDA_BAD_ARGUMENT, "NULL input");
-    const int32_t* stride = in_strides ? in_strides[i] : nullptr;
-    status = check_strides(stride, plan->extent, dim, prog.info.input_names[i]);
-    if (status != SODA_CUDA_OK) return status;
-    status = plan_alloc(plan, &plan->d_in[i], prog.in_elem_bytes[i]);
-    if (status != SODA_CUDA_OK) return status;
-  }
-  for (int o = 0; o < prog.info.num_outputs; ++o) {
-    if (out_ptrs[o] == nullptr) return fail(SODA_CUDA_BAD_ARGUMENT, "NULL output");
-    const int32_t* stride = out_strides ? out_strides[o] : nullptr;
-    status = check_strides(stride, plan->extent, dim, prog.info.output_names[o]);
-    if (status != SODA_CUDA_OK) return status;
-    status = plan_alloc(plan, &plan->d_out[o], prog.out_elem_bytes[o]);
-    if (status != SODA_CUDA_OK) return status;
-  }
-  // ---- chunked pipeline along the streamed dimension ----------------------
-  // chunk k: H2D (copy-in stream) -> all passes on its window (plan stream) ->
-  // D2H of its valid interior (copy-out stream); the copies of neighbouring
-  // chunks overlap the compute.  Chunks overlap by the total reach of all
-  // passes, so the price is (reach / chunk) redundant compute.
-  const int s_dim = dim - 1;
-  const int total = plan->extent[s_dim];
-  int reach = 0;
-  for (int pass = 0; pass < prog.info.num_passes; ++pass) {
-    const soda_cuda_pass_info& info = prog.impls[prog.schedule[pass]].info;
-    reach += std::max(0, info.reach_hi[s_dim]) + std::max(0, -info.reach_lo[s_dim]);
-  }
-  long long bytes = 0;
-  for (int i = 0; i < prog.info.num_inputs; ++i)
-    bytes += plan_cells(plan, dim) * prog.in_elem_bytes[i];
-  int chunks = plan->host_chunks;
-  if (chunks <= 0) {
-    chunks = 1;
-    if (bytes >= (32LL << 20)) {
-      // chunks of at least 8x the reach: at most 12.5 % redundant compute at
-      // the seams, and windows tall enough to fill the GPU (32 chunks of the
-      // 16384^2 x 64 workload were measured slower than 16: 30.9 vs 25.8 ms)
-      chunks = total / (8 * (reach > 0 ? reach : 1));
-      if (chunks > 16) chunks = 16;
-      if (chunks < 1) chunks = 1;
-    }
-  }
-  if (chunks > total) chunks = total;
-
-  int lo[kMaxT][kMaxD], hi[kMaxT][kMaxD];
-  default_boxes(prog, plan->extent, true, lo, hi);
-  if (chunks == 1) {
+  const int total = plan->extent[dim - 1];
+  if (HostPipeline::choose_chunks(prog, plan, total) == 1) {
+    int lo[kMaxT][kMaxD], hi[kMaxT][kMaxD];
+    default_boxes(prog, plan, true, lo, hi);
     for (int i = 0; i < prog.info.num_inputs; ++i) {
       status = copy_box(plan, plan->stream, dim, plan->d_in[i],
                         const_cast<void*>(in_ptrs[i]),
@@ -974,95 +1226,23 @@ int soda_cuda_plan_run_host(soda_cuda_plan* plan, const void* const* in_ptrs,
     return SODA_CUDA_OK;
   }
 
-  if (plan->copy_in_stream == nullptr) {
-    SODA_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->copy_in_stream,
-                                              cudaStreamNonBlocking));
-    SODA_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->copy_out_stream,
-                                              cudaStreamNonBlocking));
-  }
-  std::vector<int> bound(chunks + 1);
-  for (int k = 0; k <= chunks; ++k)
-    bound[k] = static_cast<int>(static_cast<long long>(total) * k / chunks);
-  std::vector<cudaEvent_t> copied(chunks), computed(chunks);
-  for (int k = 0; k < chunks; ++k) {
-    SODA_CUDA_CHECK(cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming));
-    SODA_CUDA_CHECK(cudaEventCreateWithFlags(&computed[k], cudaEventDisableTiming));
-  }
-  int result = SODA_CUDA_OK;
-  // the copy-in stream must not run ahead of work already queued on the plan
-  // stream that still reads the staging buffers (a previous call)
-  cudaEvent_t start_event;
-  SODA_CUDA_CHECK(cudaEventCreateWithFlags(&start_event, cudaEventDisableTiming));
-  SODA_CUDA_CHECK(cudaEventRecord(start_event, plan->stream));
-  SODA_CUDA_CHECK(cudaStreamWaitEvent(plan->copy_in_stream, start_event, 0));
-  for (int k = 0; k < chunks && result == SODA_CUDA_OK; ++k) {
-    int c_lo[kMaxD] = {0, 0, 0}, c_hi[kMaxD];
-    for (int d = 0; d < dim; ++d) c_hi[d] = plan->extent[d];
-    c_lo[s_dim] = bound[k];
-    c_hi[s_dim] = bound[k + 1];
-    for (int i = 0; i < prog.info.num_inputs && result == SODA_CUDA_OK; ++i)
-      result = copy_box(plan, plan->copy_in_stream, dim, plan->d_in[i],
-                        const_cast<void*>(in_ptrs[i]),
-                        in_strides ? in_strides[i] : nullptr,
-                        prog.in_elem_bytes[i], c_lo, c_hi, true);
-    if (result == SODA_CUDA_OK &&
-        cudaEventRecord(copied[k], plan->copy_in_stream) != cudaSuccess)
-      result = fail(SODA_CUDA_CUDA_ERROR, "cudaEventRecord failed");
-  }
-  int reach_hi_total = 0;
-  for (int pass = 0; pass < prog.info.num_passes; ++pass)
-    reach_hi_total +=
-        std::max(0, prog.impls[prog.schedule[pass]].info.reach_hi[s_dim]);
-  for (int k = 0; k < chunks && result == SODA_CUDA_OK; ++k) {
-    // the window of chunk k ends at bound[k+1] + reach_hi: wait for the last
-    // chunk it touches (copies are issued in order on one stream)
-    int last_needed = k;
-    while (last_needed + 1 < chunks &&
-           bound[last_needed + 1] < bound[k + 1] + reach_hi_total)
-      ++last_needed;
-    if (cudaStreamWaitEvent(plan->stream, copied[last_needed], 0) != cudaSuccess)
-      result = fail(SODA_CUDA_CUDA_ERROR, "cudaStreamWaitEvent failed");
-    if (result == SODA_CUDA_OK)
-      result = run_passes_window(plan, plan->d_in, pitches, plan->d_out, pitches,
-                                 bound[k], bound[k + 1]);
-    if (result != SODA_CUDA_OK) break;
-    if (cudaEventRecord(computed[k], plan->stream) != cudaSuccess ||
-        cudaStreamWaitEvent(plan->copy_out_stream, computed[k], 0) != cudaSuccess)
-      result = fail(SODA_CUDA_CUDA_ERROR, "event synchronisation failed");
-    for (int o = 0; o < prog.info.num_outputs && result == SODA_CUDA_OK; ++o) {
-      int o_lo[kMaxD], o_hi[kMaxD];
-      bool empty = false;
-      for (int d = 0; d < dim; ++d) {
-        o_lo[d] = lo[o][d];
-        o_hi[d] = hi[o][d];
-      }
-      if (o_lo[s_dim] < bound[k]) o_lo[s_dim] = bound[k];
-      if (o_hi[s_dim] > bound[k + 1]) o_hi[s_dim] = bound[k + 1];
-      for (int d = 0; d < dim; ++d) empty = empty || o_hi[d] <= o_lo[d];
-      if (empty) continue;
-      result = copy_box(plan, plan->copy_out_stream, dim, plan->d_out[o],
-                        out_ptrs[o], out_strides ? out_strides[o] : nullptr,
-                        prog.out_elem_bytes[o], o_lo, o_hi, false);
-    }
-  }
-  cudaError_t sync_in = cudaStreamSynchronize(plan->copy_in_stream);
-  cudaError_t sync_compute = cudaStreamSynchronize(plan->stream);
-  cudaError_t sync_out = cudaStreamSynchronize(plan->copy_out_stream);
-  for (int k = 0; k < chunks; ++k) {
-    cudaEventDestroy(copied[k]);
-    cudaEventDestroy(computed[k]);
-  }
-  cudaEventDestroy(start_event);
-  if (result != SODA_CUDA_OK) return result;
-  SODA_CUDA_CHECK(sync_in);
-  SODA_CUDA_CHECK(sync_compute);
-  SODA_CUDA_CHECK(sync_out);
-  return SODA_CUDA_OK;
+  HostPipeline pipe;
+  pipe.plan = plan;
+  pipe.in_ptrs = in_ptrs;
+  pipe.in_strides = in_strides;
+  pipe.out_ptrs = out_ptrs;
+  pipe.out_strides = out_strides;
+  pipe.own_lo = pipe.host_lo = 0;
+  pipe.own_hi = pipe.host_hi = total;
+  return pipe.finish(pipe.issue());
 }
 
 int soda_cuda_run_host(const void* const* in_ptrs, const int32_t* const* in_strides,
                        void* const* out_ptrs, const int32_t* const* out_strides,
                        const int32_t* extent, const soda_cuda_opts* opts) {
+  if (opts != nullptr && opts->reserved[1] > 1)  // sodac --cuda-gpus N
+    return soda_cuda_multi_run_host(in_ptrs, in_strides, out_ptrs, out_strides,
+                                    extent, nullptr, opts->reserved[1], opts);
   soda_cuda_plan* plan = nullptr;
   int status = soda_cuda_plan_create(extent, opts, &plan);
   if (status != SODA_CUDA_OK) return status;
@@ -1111,10 +1291,20 @@ int soda_cuda_run_pass(int32_t pass_index, const int32_t* extent,
   } else {
     int ext[kMaxD] = {0, 0, 0};
     for (int d = 0; d < prog.info.dim; ++d) ext[d] = extent[d];
-    default_boxes(prog, ext, pass_index == prog.info.num_passes - 1, a.box_lo,
+    soda_cuda_plan whole;
+    memset(&whole, 0, sizeof(whole));
+    for (int d = 0; d < prog.info.dim; ++d) whole.extent[d] = ext[d];
+    for (int o = 0; o < prog.info.num_outputs; ++o) {
+      whole.s_valid_lo[o] = prog.info.final_lo[o][prog.info.dim - 1];
+      whole.s_valid_hi[o] =
+          ext[prog.info.dim - 1] - prog.info.final_hi[o][prog.info.dim - 1];
+    }
+    default_boxes(prog, &whole, pass_index == prog.info.num_passes - 1, a.box_lo,
                   a.box_hi);
   }
   return launch_tuned(prog, prog.schedule[pass_index], a);
 }
 
 }  // extern "C"
+
+#include "soda_slab.cuh"

@@ -52,7 +52,8 @@ struct dim3 {
 
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+// several emulated devices, so that the multi-device host path can be driven
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 4; return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
@@ -97,6 +98,10 @@ inline cudaError_t cudaMalloc(void** ptr, size_t bytes) {
   return cudaSuccess;
 }
 inline cudaError_t cudaFree(void* ptr) { free(ptr); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* ptr, int value, size_t bytes, cudaStream_t) {
+  memset(ptr, value, bytes);
+  return cudaSuccess;
+}
 template <class K>
 cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class K>
