@@ -57,12 +57,16 @@ CONFIGS = {
     'C4_denoise3d_cr': dict(program='denoise3d',
                             overrides={'computation_reuse': 'yes'},
                             extent=(512, 512, 512)),
+    # the same program with sqrt(float) kept in float (--math-precision float)
+    'C4_denoise3d_float_math': dict(program='denoise3d',
+                                    overrides={'math_precision': 'float'},
+                                    extent=(512, 512, 512)),
     'C5_jacobi2d': dict(program='jacobi2d', overrides={'iterate': 256},
                         extent=(65536, 65536)),
 }
 HEADLINE = 'C2_jacobi2d'
 OTHER = ('C1_blur', 'C3_heat3d', 'C3_jacobi3d', 'C4_denoise3d',
-         'C4_denoise3d_cr')
+         'C4_denoise3d_cr', 'C4_denoise3d_float_math')
 WIDTH, HEIGHT = CONFIGS[HEADLINE]['extent']
 ITERATE = CONFIGS[HEADLINE]['overrides']['iterate']
 PROGRAM = CONFIGS[HEADLINE]['program']
@@ -428,8 +432,10 @@ def run_device_config(key, device, stream, steps, warmup, peak, windows=8):
       'config': key,
       'workload': '%s %s iterate %d%s' %
                   (CONFIGS[key]['program'], 'x'.join(map(str, extent)),
-                   st.iterate, ' --computation-reuse'
-                   if CONFIGS[key]['overrides'].get('computation_reuse') else ''),
+                   st.iterate, ''.join(
+                       ' --%s %s' % (k.replace('_', '-'), v)
+                       for k, v in CONFIGS[key]['overrides'].items()
+                       if k != 'iterate')),
       'value': gcells,
       'unit': 'Gcell-updates/s',
       'ms_per_step': ms,

@@ -148,6 +148,8 @@ class _Evaluator:
             'pow': np.power,
         }.get(node.name) or getattr(np, node.name)
         with np.errstate(all='ignore'):
+          if node.haoda_type == ir.FLOAT:  # float math mode
+            return func(_as(args[0][0], ir.FLOAT)).astype(np.float32), ir.FLOAT
           return func(*[_as(v, ir.DOUBLE) for v, _ in args]), ir.DOUBLE
       if node.name in ir.SELECT_CALLS:
         t = args[0][1]

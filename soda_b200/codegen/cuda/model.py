@@ -3,12 +3,20 @@ block) pair and which time block the planner should pick.
 
 The reference sizes its accelerator the same way (reference:
 src/soda/model/xilinx.py:131-144): performance = min(compute rate, DRAM
-bandwidth / bytes per cell) x iterate.  Here, per pass variant:
+bandwidth / bytes per cell) x iterate.  Here, per pass variant and per cell:
 
-  hbm    = HBM peak x eff / (bytes per cell per pass) x fused iterations
-  fma    = fp32 lanes / (fp32 operations per update x halo redundancy)
-  issue  = issue slots / (thread-instructions per update x halo redundancy)
-  rate   = min(hbm, fma, issue)
+  t_hbm   = bytes per cell per pass / HBM streaming rate
+  t_fma   = fp32 operations per update x fused iterations x halo redundancy
+            / (fp32 lanes x efficiency)
+  t_issue = thread-instructions per update x fused iterations x halo
+            redundancy / (issue slots x efficiency)
+  t_pass  = (t_hbm^3 + t_fma^3 + t_issue^3)^(1/3)
+
+The cubic norm instead of a plain maximum is what the measured sweep shows
+(profiles/r02_time_block_sweep.jsonl): loads, arithmetic and stores of one
+warp overlap only partly, so a pass slows down before it reaches either
+ceiling (jacobi2d: 0.316 / 0.355 / 0.383 / 0.438 / 0.479 ms per pass at time
+blocks 1 / 4 / 6 / 7 / 8; the norm gives 0.316 / 0.346 / 0.401 / 0.438 / 0.478).
 
 * *halo redundancy*: cells a strip / tile computes per cell it stores; grows
   with the time block because the halo does (``strip / valid``), and jumps
@@ -21,13 +29,16 @@ bandwidth / bytes per cell) x iterate.  Here, per pass variant:
   Packed fp32 / binary16 pairs halve the arithmetic issue slots, not the FMA
   pipe time (FADD2 holds the pipe two cycles).
 * efficiencies are the fractions of each ceiling the shipped kernels reach on
-  B200 (profiles/r01_ncu_full_*_summary.txt): 0.90 of the measured copy peak,
-  0.68 of the FMA pipe, 0.70 of the issue slots.
+  B200, fitted on the sweep: streaming stencils move 1.04 x the measured copy
+  peak (less read/write turnaround than a copy); packed pairs keep the FMA
+  pipe 0.72 busy with 8-cell lanes and 0.67 with 4-cell ones; scalar programs
+  issue at 0.95 of the slots while at least three warps per scheduler are
+  resident and at 0.67 below that (seidel2d from time block 5 on); 3-D CTAs
+  issue at 0.80 with four-warp CTAs and 0.60 with larger ones (one CTA barrier
+  per plane); every pass pays 8 us of launch.
 
-The constants are validated against the measured sweep in
-profiles/r02_time_block_sweep.jsonl (tests/test_model.py): the model only has
-to rank time blocks, and its choice must be within a few per cent of the
-measured best.
+The model only has to rank time blocks: tests/test_model.py checks that its
+choice is within a few per cent of the measured best on every swept program.
 """
 from typing import Dict, List, Optional
 
@@ -40,16 +51,16 @@ LANES_PER_SM = 128
 SM_GHZ = 1.965
 LANE_RATE = SM_COUNT * LANES_PER_SM * SM_GHZ * 1e9  # thread-instr / s
 
-HBM_EFF = 0.90
-# fraction of the FMA pipe / issue slots the kernels reach.  Lanes of 8 cells
-# carry twice the independent chains of 4-cell lanes at the same (low)
-# occupancy: jacobi2d reaches 0.68 of the pipe at time block 6 (8 cells) and
-# 0.60 at time block 8 (4 cells).  3-D CTAs meet at one barrier per plane; the
-# more warps wait at it the fewer issue slots are used (jacobi3d: 0.61 with 4
-# warps at time block 2, 0.49 with 12 at time block 3).
-FMA_EFF = {8: 0.68, 4: 0.60}
-ISSUE_EFF = 0.70
-BARRIER_LOSS_PER_WARP = 0.025  # 3-D, per warp beyond 4
+HBM_EFF = 1.04
+FMA_EFF = {8: 0.72, 4: 0.67}
+ISSUE_EFF = 0.95
+ISSUE_EFF_LOW_OCCUPANCY = 0.67   # fewer than three warps per scheduler
+# 3-D CTAs meet at one barrier per plane: four-warp CTAs, several per SM, hide
+# it; the 12-16 warps of a time-block-3/4 tile wait for each other
+ISSUE_EFF_3D = {True: 0.80, False: 0.60}   # keyed by (warps per CTA <= 4)
+LAUNCH_SECONDS = 8e-6            # per pass: launch latency, ramp-up, tail
+NORM = 3.0
+REGISTER_FILE = 65536
 # thread-instructions per lane and step that do not depend on the program:
 # input vector load from the TMA ring, store, pointer bumps, barrier / mbarrier
 STEP_OVERHEAD_2D = 1.0   # per cell of the lane, per pass
@@ -175,16 +186,33 @@ def estimate_pass(stencil, time_block: int,
 
   bytes_per_cell = sum(t.width_in_bits // 8 for t in stencil.input_types +
                        stencil.output_types)
-  hbm = HBM_GBS * 1e9 * HBM_EFF / bytes_per_cell * time_block
-  issue_eff = ISSUE_EFF
+  # resident warps per scheduler, from the register estimate
+  threads = (tuning_warps(pp) or 4) * 32
+  ctas = max(1, REGISTER_FILE // (min(registers, MAX_REGISTERS) * threads))
+  warps_per_scheduler = ctas * threads / 32 / 4.0
   if dim == 3:
-    warps = pp.rows // cy
-    issue_eff *= max(0.4, 1.0 - BARRIER_LOSS_PER_WARP * max(0, warps - 4))
-  fma_eff = FMA_EFF.get(cells, FMA_EFF[4] if cells < 8 else FMA_EFF[8])
-  issue = LANE_RATE * issue_eff / (instr * redundancy)
-  fma = LANE_RATE * fma_eff / (max(fp, 1e-9) * redundancy)
-  rate = min(hbm, issue, fma)
-  bound = 'hbm' if rate == hbm else ('issue' if rate == issue else 'fma')
+    issue_eff = ISSUE_EFF_3D[pp.rows // cy <= 4]
+  elif pp.pack == 1 and warps_per_scheduler < 3.0:
+    issue_eff = ISSUE_EFF_LOW_OCCUPANCY
+  else:
+    issue_eff = ISSUE_EFF
+  fma_eff = FMA_EFF[8] if cells >= 8 else FMA_EFF[4]
+  if pp.pack == 1:
+    fma_eff = 1.0  # scalar FADD / FMUL: one pipe cycle each, the issue slots bind
+
+  # seconds per grid cell and pass
+  t_hbm = bytes_per_cell / (HBM_GBS * 1e9 * HBM_EFF)
+  t_issue = instr * time_block * redundancy / (LANE_RATE * issue_eff)
+  t_fma = fp * time_block * redundancy / (LANE_RATE * fma_eff)
+  t_pass = (t_hbm ** NORM + t_issue ** NORM + t_fma ** NORM) ** (1.0 / NORM)
+  if extent is not None:
+    # small grids (C1: 2000 x 16384 cells take 30 us per pass) feel the launch
+    grid_cells = 1
+    for e in extent:
+      grid_cells *= e
+    t_pass += LAUNCH_SECONDS / grid_cells
+  rate = time_block / t_pass
+  bound = max((t_hbm, 'hbm'), (t_issue, 'issue'), (t_fma, 'fma'))[1]
   return {
       'time_block': time_block,
       'cells': cells,
@@ -192,15 +220,26 @@ def estimate_pass(stencil, time_block: int,
       'rows': pp.rows,
       'pack': pp.pack,
       'window_registers': window * cells * cy,
+      'registers': registers,
+      'warps_per_scheduler': warps_per_scheduler,
       'redundancy': redundancy,
       'instr_per_update': instr,
       'fp_per_update': fp,
-      'hbm_ceiling_gcells': hbm / 1e9,
+      'hbm_ceiling_gcells': time_block / t_hbm / 1e9,
       'issue_ceiling_gcells': LANE_RATE / (instr * redundancy) / 1e9,
       'fma_ceiling_gcells': LANE_RATE / (max(fp, 1e-9) * redundancy) / 1e9,
+      'ms_per_gcell_pass': t_pass * 1e12,
       'gcells': rate / 1e9,
       'bound': bound,
   }
+
+
+def tuning_warps(pp) -> int:
+  """Warps per CTA of a pass plan (the emitter's launch shape)."""
+  from soda_b200.codegen.cuda import emit
+  if pp.dim == 2:
+    return emit.tuning_2d(pp, {})['kWarps']
+  return pp.rows // pp.cy
 
 
 def estimate(stencil, time_block: int, options: Optional[Dict] = None,
@@ -233,7 +272,7 @@ def choose_time_block(stencil, options: Optional[Dict] = None,
                       extent: Optional[List[int]] = None,
                       limit: int = 12) -> int:
   """The time block with the highest modelled throughput; ties and near-ties
-  (within 2 %) go to the smaller one (shorter halos, shorter warm-up).
+  (within 3 %) go to the smaller one (shorter halos, shorter warm-up).
   ``extent`` (or ``options['extent_hint']``) is the grid the library will
   mostly run on; the program itself does not fix one."""
   extent = extent or (options or {}).get('extent_hint') or \
@@ -243,6 +282,6 @@ def choose_time_block(stencil, options: Optional[Dict] = None,
     est = estimate(stencil, tb, options, extent)
     if est is None:
       continue
-    if best is None or est['gcells'] > best * 1.02:
+    if best is None or est['gcells'] > best * 1.03:
       best_tb, best = tb, est['gcells']
   return best_tb

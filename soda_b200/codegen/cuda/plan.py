@@ -517,7 +517,14 @@ def make_tuned_pass_plan(stencil, time_block: int,
     # slower on B200 for every program tried: blur time block 2 1577 vs 1791
     # Gcell-updates/s, sobel2d 1382 vs 1451, half jacobi2d time block 6 4368
     # vs 4826 (profiles/r01_lanes16.jsonl)
-    if cells is None and probe.cells * 2 * window <= 160 and all(
+    # register budget of 8-cell lanes: packed pair arithmetic needs few
+    # temporaries (jacobi2d time block 8: 200 window registers, 252 in all, no
+    # spill, 4483 against 3941 Gcell-updates/s with 4-cell lanes); scalar
+    # arithmetic slows down well before it spills (seidel2d time block 5: 128
+    # window registers, 199 in all, 0.64 ms per pass against 0.41 at time
+    # block 4 - profiles/r02_time_block_sweep.jsonl)
+    budget = 200 if probe.pack == 2 else 160
+    if cells is None and probe.cells * 2 * window <= budget and all(
         t.width_in_bits == 32 for t in stencil.input_types +
         stencil.output_types + tuple(stencil.local_types)):
       cells = probe.cells * 2

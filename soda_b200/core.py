@@ -78,6 +78,11 @@ class Stencil:
     self.local_stmts = list(kwargs.pop('local_stmts', ()) or ())
     self.output_stmts = list(kwargs.pop('output_stmts'))
     self.optimizations = dict(kwargs.pop('optimizations', None) or {})
+    # 'double' (default) or 'float': see ir.FLOAT_MATH_CALLS
+    self.math_precision = kwargs.pop('math_precision', None) or 'double'
+    if self.math_precision not in ('double', 'float'):
+      raise util.SemanticError('math precision must be double or float')
+    self.float_math = self.math_precision == 'float'
 
     self._override_dram(kwargs.pop('dram_in', None), self.input_stmts, '^',
                         'input')
@@ -241,7 +246,7 @@ class Stencil:
 
     def propagate(node, stmt=None):
       table = self.symbol_table if stmt is None else stmt.symbol_table
-      return ir.propagate_type(node, table)
+      return ir.propagate_type(node, table, self.float_math)
 
     return propagate
 

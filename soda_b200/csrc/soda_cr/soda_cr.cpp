@@ -382,6 +382,84 @@ PatternPtr Search(const std::vector<Item>& start, int beam_width, int branch,
   return best;
 }
 
+// ---- exhaustive search (--optimal) -----------------------------------------------
+// Every binary tree over the operands, as the reference's CommSchedules does
+// (reference :983-1059: the first operand stays in the left child, every
+// subset of the others joins it, both children are expanded recursively), with
+// the running count of distinct sub-trees as the pruning cost (the reference's
+// "skip-with-partial-cost").  (2n-3)!! trees: exact up to 9 operands in
+// seconds; beyond that the node budget ends the search, the best tree so far
+// is returned and "proven_optimal" is false (the reference gives up after a
+// 300 s timeout in the same way).  All trees with the fewest operations are
+// kept (up to a cap) so that the caller can break the tie by total reuse
+// distance, the second component of the reference's cost.
+struct Exhaustive {
+  std::vector<long long> rattrs, aattrs;  // sorted by rattr
+  int best_ops = 1 << 30;
+  std::vector<PatternPtr> best_trees;
+  std::set<std::string> best_texts;
+  std::map<Leaves, int, LeavesLess> live;  // distinct sub-trees on the DFS path
+  long long nodes = 0, node_limit = 0;
+  bool complete = true;
+  size_t cap = 4096;
+
+  static std::string Text(const PatternPtr& p) {
+    if (p->is_leaf()) return std::to_string(p->leaves[0].second);
+    return "(" + Text(p->left) + "=" + std::to_string(p->distance) + "=" +
+           Text(p->right) + ")";
+  }
+
+  // (std::function, not a template: every nesting level would be a new type)
+  using Cont = std::function<void(const PatternPtr&)>;
+  void Enumerate(const std::vector<int>& set, const Cont& cont) {
+    if (!complete) return;
+    if (set.size() == 1) {
+      cont(MakeLeaf(aattrs[set[0]]));
+      return;
+    }
+    const int n = static_cast<int>(set.size());
+    // subsets of set[1..] that join set[0] on the left; not all of them
+    for (unsigned mask = 0; mask + 1 < (1u << (n - 1)); ++mask) {
+      std::vector<int> left{set[0]}, right;
+      for (int i = 1; i < n; ++i)
+        ((mask >> (i - 1)) & 1u ? left : right).push_back(set[i]);
+      const long long distance = rattrs[right[0]] - rattrs[left[0]];
+      Enumerate(left, [&](const PatternPtr& l) {
+        Enumerate(right, [&](const PatternPtr& r) {
+          if (++nodes > node_limit) {
+            complete = false;
+            return;
+          }
+          PatternPtr merged = Merge(l, r, distance);
+          int& count = live[merged->leaves];
+          ++count;
+          // one more operation is certain unless this is the whole tree
+          const int ops = static_cast<int>(live.size());
+          const bool whole = merged->leaves.size() == rattrs.size();
+          if (ops + (whole ? 0 : 1) <= best_ops) cont(merged);
+          if (--live[merged->leaves] == 0) live.erase(merged->leaves);
+        });
+      });
+    }
+  }
+
+  void Run() {
+    std::vector<int> all(rattrs.size());
+    for (size_t i = 0; i < all.size(); ++i) all[i] = static_cast<int>(i);
+    Enumerate(all, [&](const PatternPtr& tree) {
+      const int ops = static_cast<int>(live.size());
+      if (ops < best_ops) {
+        best_ops = ops;
+        best_trees.clear();
+        best_texts.clear();
+      }
+      if (ops == best_ops && best_trees.size() < cap &&
+          best_texts.insert(Text(tree)).second)
+        best_trees.push_back(tree);
+    });
+  }
+};
+
 void PrintTree(const PatternPtr& p, std::ostream& out) {
   if (p->is_leaf()) {
     out << p->leaves[0].second;
@@ -398,6 +476,7 @@ void PrintTree(const PatternPtr& p, std::ostream& out) {
 
 int main(int argc, char** argv) {
   int beam_width = 6, branch = 4;
+  bool optimal = false;
   for (int i = 1; i < argc; ++i) {
     std::string flag = argv[i];
     if (flag == "--greedy") {
@@ -409,8 +488,12 @@ int main(int argc, char** argv) {
     } else if (flag == "--brute-force") {
       beam_width = 256;
       branch = 32;
+    } else if (flag == "--optimal") {
+      optimal = true;
+      beam_width = 256;  // the beam result seeds the pruning bound
+      branch = 32;
     } else if (flag == "--help") {
-      std::cout << "usage: soda-cr [--greedy|--beam|--brute-force] < in.json\n";
+      std::cout << "usage: soda-cr [--greedy|--beam|--brute-force|--optimal] < in.json\n";
       return 0;
     }
   }
@@ -444,6 +527,34 @@ int main(int argc, char** argv) {
   for (size_t i = 0; i < n; ++i)
     start.push_back(Item{in.rattrs[i], MakeLeaf(in.aattrs[i])});
   PatternPtr best = Search(start, beam_width, branch, linearizer);
+  std::vector<PatternPtr> alternatives;
+  bool proven = false;
+  long long nodes = 0;
+  if (optimal) {
+    Exhaustive search;
+    std::vector<size_t> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+      return in.rattrs[a] < in.rattrs[b];
+    });
+    for (size_t i : order) {
+      search.rattrs.push_back(in.rattrs[i]);
+      search.aattrs.push_back(in.aattrs[i]);
+    }
+    search.best_ops = NumOps(best);
+    const char* limit = getenv("SODA_CR_NODE_LIMIT");
+    search.node_limit = limit ? atoll(limit) : 40000000LL;
+    search.Run();
+    proven = search.complete;
+    nodes = search.nodes;
+    if (!search.best_trees.empty()) {
+      best = search.best_trees[0];
+      alternatives.assign(search.best_trees.begin() + 1, search.best_trees.end());
+    }
+    if (!proven)
+      std::cerr << "soda-cr: --optimal stopped after " << nodes
+                << " trees; the schedule is the best found, not proven optimal\n";
+  }
   std::vector<long long> sorted_rattrs = in.rattrs;
   std::sort(sorted_rattrs.begin(), sorted_rattrs.end());
   std::cout << "{\"rattrs\": [";
@@ -453,6 +564,16 @@ int main(int argc, char** argv) {
   PrintTree(best->left, std::cout);
   std::cout << ", \"right\": ";
   PrintTree(best->right, std::cout);
-  std::cout << ", \"distance\": " << best->distance << "}\n";
+  std::cout << ", \"distance\": " << best->distance;
+  if (optimal) {
+    std::cout << ", \"proven_optimal\": " << (proven ? "true" : "false")
+              << ", \"trees\": " << nodes << ", \"alternatives\": [";
+    for (size_t i = 0; i < alternatives.size(); ++i) {
+      std::cout << (i ? ", " : "");
+      PrintTree(alternatives[i], std::cout);
+    }
+    std::cout << "]";
+  }
+  std::cout << "}\n";
   return 0;
 }

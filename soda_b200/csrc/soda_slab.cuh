@@ -633,9 +633,13 @@ int soda_cuda_slab_exchange_inputs(soda_cuda_slab* slab, int32_t depth_lo,
   const ProgramDesc& prog = soda_program();
   if (slab == nullptr || slab->dry_run)
     return fail(SODA_CUDA_BAD_ARGUMENT, "slab is NULL or a dry run");
-  if (depth_lo < 0 || depth_hi < 0 || depth_lo > slab->own_lo ||
-      (slab->rank < slab->world - 1 &&
-       depth_hi > slab->plan->extent[prog.info.dim - 1] - slab->own_hi))
+  // a side without a neighbour has no ghost and takes no part in the exchange
+  const bool below = slab->rank > 0, above = slab->rank < slab->world - 1;
+  if (depth_lo < 0 || depth_hi < 0 || (below && depth_lo > slab->own_lo) ||
+      (above &&
+       depth_hi > slab->plan->extent[prog.info.dim - 1] - slab->own_hi) ||
+      depth_lo > slab->own_hi - slab->own_lo ||
+      depth_hi > slab->own_hi - slab->own_lo)
     return fail(SODA_CUDA_BAD_ARGUMENT, "exchange deeper than the ghost");
   DeviceGuard guard;
   int status = guard.enter(slab->plan->device);

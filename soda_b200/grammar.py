@@ -143,7 +143,8 @@ class LocalStmtOrOutputStmt(ir.Node):
         if let.haoda_type is not None:
           table[name] = let.haoda_type
         else:
-          table[name] = ir.propagate_type(let.expr, table).haoda_type
+          table[name] = ir.propagate_type(let.expr, table,
+                                          self._float_math).haoda_type
         del pending[name]
         progress = True
     if pending:
@@ -155,10 +156,15 @@ class LocalStmtOrOutputStmt(ir.Node):
     """Type every node; wrap the expression in a Cast to the declared tensor
     type if it differs (reference: src/soda/grammar.py:123-136)."""
     table = self.symbol_table
-    self.expr = ir.propagate_type(self.expr, table)
+    self.expr = ir.propagate_type(self.expr, table, self._float_math)
     if self.expr.haoda_type != self.haoda_type:
       self.expr = ir.Cast(expr=self.expr, haoda_type=self.haoda_type)
-    self.let = tuple(ir.propagate_type(let, table) for let in self.let)
+    self.let = tuple(ir.propagate_type(let, table, self._float_math)
+                     for let in self.let)
+
+  @property
+  def _float_math(self) -> bool:
+    return bool(getattr(getattr(self, 'stencil', None), 'float_math', False))
 
 
 class LocalStmt(LocalStmtOrOutputStmt):

@@ -515,6 +515,15 @@ def get_vars(node: Node) -> Tuple[Var, ...]:
 # with g++ 13.3: decltype(sqrt(1.0f)) is double).
 DOUBLE_MATH_CALLS = ('sqrt', 'exp', 'log', 'fabs', 'floor', 'ceil', 'pow',
                      'sin', 'cos', 'tanh')
+# ... unless the float overloads are visible in the global namespace: the
+# reference's generated files also include Xilinx's <ap_int.h>
+# (src/soda/codegen/frt/host.py:33, xilinx/hls_kernel.py:228-233), which is not
+# on disk here and may pull ``std::sqrt(float)`` and friends into scope.  The
+# ``float`` math mode (sodac --math-precision float) models that reading: these
+# calls - the ones that are correctly rounded in binary32 on both the CPU and
+# the GPU - keep a float argument in float.  The default stays double, the
+# behaviour that can be checked here (plain <cmath>, g++ 13.3).
+FLOAT_MATH_CALLS = ('sqrt', 'fabs', 'floor', 'ceil')
 SELECT_CALLS = ('min', 'max')
 
 
@@ -526,10 +535,13 @@ def result_type(node: Node) -> Type:
   return t
 
 
-def propagate_type(node: Node, symbol_table: Dict[str, Type]) -> Node:
+def propagate_type(node: Node, symbol_table: Dict[str, Type],
+                   float_math: bool = False) -> Node:
   """Returns a copy of ``node`` with ``haoda_type`` set on every sub-node.
 
   ``symbol_table`` maps tensor names and let-variable names to their types.
+  ``float_math``: ``sqrt`` / ``fabs`` / ``floor`` / ``ceil`` of a ``float``
+  stay ``float`` (see ``FLOAT_MATH_CALLS``) instead of going through double.
   """
 
   def post(obj, args):
@@ -563,7 +575,11 @@ def propagate_type(node: Node, symbol_table: Dict[str, Type]) -> Node:
       obj.haoda_type = t
     elif isinstance(obj, Call):
       if obj.name in DOUBLE_MATH_CALLS:
-        obj.haoda_type = DOUBLE
+        if float_math and obj.name in FLOAT_MATH_CALLS and all(
+            result_type(arg) == FLOAT for arg in obj.arg):
+          obj.haoda_type = FLOAT
+        else:
+          obj.haoda_type = DOUBLE
       elif obj.name in SELECT_CALLS:
         t = result_type(obj.arg[0])
         for arg in obj.arg[1:]:
@@ -631,6 +647,8 @@ class CPrinter:
           result = '{}<{}>({}, {}({}))'.format(name, ctype, result, ctype, arg)
         return result
       if node.name in DOUBLE_MATH_CALLS:
+        if node.haoda_type == FLOAT:  # float math mode
+          return '{}f(float({}))'.format(node.name, args[0])
         return '{}(double({}){})'.format(
             node.name, args[0],
             ''.join(', double(%s)' % a for a in args[1:]))

@@ -237,7 +237,8 @@ def _disjoint_occurrences(items: Sequence[Item], left: Pattern,
   return found
 
 
-def _candidate_moves(items: Sequence[Item], limit: int):
+def _candidate_moves(items: Sequence[Item], limit: int,
+                     axis_order: Optional[Sequence[int]] = None):
   """Pair patterns that occur at least twice without overlap, best first."""
   counts = collections.Counter()
   for a, b in itertools.combinations(items, 2):
@@ -265,7 +266,8 @@ def _candidate_moves(items: Sequence[Item], limit: int):
   # like the reference's greedy search (:1262-1276), also follow reuse along a
   # single dimension, highest dimension first: it keeps grids regular
   dim = len(items[0][0])
-  for axis in reversed(range(dim)):
+  for axis in (axis_order if axis_order is not None else
+               tuple(reversed(range(dim)))):
     aligned = [
         (key, count) for key, count in ranked if count >= 2 and
         key[2][axis] != 0 and all(key[2][d] == 0 for d in range(dim)
@@ -332,6 +334,142 @@ def total_distance(tree: Pattern) -> int:
   return total
 
 
+def reuse_dependencies(tree: Pattern, weights: Sequence[int]):
+  """Dependency tables between the reused variables of a schedule, as the
+  reference computes them (reference :413-541, ``_calc_dependency``): variable
+  0 is the input, 1 the whole schedule, 2.. the sub-trees that occur more than
+  once (translation-equivalent), in pre-order of first occurrence.  A variable
+  that a single other variable reads at a single offset is inlined into it.
+
+  Returns ``(dependers, dependees)``: ``dependers[src]`` is the ordered set of
+  variables that read ``src``; ``dependees[dst][src]`` the (first, last)
+  linearised offset at which ``dst`` reads ``src``."""
+  def linear(distance: Index) -> int:
+    return sum(d * w for d, w in zip(distance, weights))
+
+  def occurrences(pattern: Pattern):
+    if pattern.is_leaf:
+      return
+    yield pattern
+    yield from occurrences(pattern.left)
+    yield from occurrences(pattern.right)
+
+  counts: Dict[Pattern, int] = collections.OrderedDict()
+  for pattern in occurrences(tree):
+    counts[pattern] = counts.get(pattern, 0) + 1
+  var_of: Dict[Pattern, int] = collections.OrderedDict([(tree, 1)])
+  table = {1: tree}
+  for pattern, count in counts.items():
+    if count > 1 and pattern not in var_of:
+      var_of[pattern] = len(var_of) + 1
+      table[len(var_of)] = pattern
+
+  def accesses(pattern: Pattern, offset: Optional[int] = None):
+    vid = var_of.get(pattern)
+    if vid is not None and offset is not None:
+      yield offset, vid
+      return
+    offset = offset or 0
+    for child, base in ((pattern.left, offset),
+                        (pattern.right, offset + linear(pattern.distance))):
+      if child.is_leaf:
+        yield base, 0
+      else:
+        yield from accesses(child, base)
+
+  dependers: Dict[int, Dict[int, None]] = collections.OrderedDict()
+  dependees: Dict[int, Dict[int, Tuple[int, int]]] = collections.OrderedDict()
+  queue = collections.deque([tree])
+  processed = {0}
+  while queue:
+    pattern = queue.popleft()
+    dst = var_of[pattern]
+    processed.add(dst)
+    for offset, src in accesses(pattern):
+      dependers.setdefault(src, collections.OrderedDict()).setdefault(dst)
+      lo, hi = dependees.setdefault(
+          dst, collections.OrderedDict()).setdefault(src, (offset, offset))
+      dependees[dst][src] = (min(lo, offset), max(hi, offset))
+      if src not in processed and table[src] not in queue:
+        queue.append(table[src])
+
+  def find_inline():
+    for src, dsts in dependers.items():
+      if len(dsts) == 1:
+        dst = next(iter(dsts))
+        lo, hi = dependees[dst][src]
+        if lo == hi:
+          return src, dst
+    return None
+
+  while True:
+    found = find_inline()
+    if found is None:
+      break
+    src, dst = found
+    offset = dependees[dst][src][0]
+    for inner, (lo, hi) in dependees.get(src, {}).items():
+      new = (lo + offset, hi + offset)
+      old = dependees[dst].get(inner, new)
+      dependees[dst][inner] = (min(old[0], new[0]), max(old[1], new[1]))
+    for inner in list(dependees.get(src, {})):
+      dependers[inner][dst] = None
+      del dependers[inner][src]
+    del dependers[src]
+    del dependees[dst][src]
+    dependees.pop(src, None)
+  return dependers, dependees
+
+
+def reference_total_distance(tree: Pattern, linearizer: 'Linearizer') -> int:
+  """The reference's ``CommSchedule.total_distance`` (reference :573-624): the
+  sum over reused variables (the input included) of the distance between the
+  offset at which a variable is first produced and the one at which it is last
+  consumed, with the produce offsets chosen by an integer program.  The
+  program has difference constraints only, so its LP relaxation (solved here
+  with scipy's HiGHS; the reference uses pulp + CBC) is integral."""
+  import numpy as np
+  from scipy.optimize import linprog
+  if tree.is_leaf:
+    return 0
+  dependers, dependees = reuse_dependencies(tree, linearizer.weights)
+  sources = list(dependers)
+  # unknowns: produce offset P_v of every source but the input (P_0 = P_1 = 0),
+  # consume offset C_v of every source
+  p_index = {v: i for i, v in enumerate(v for v in sources if v not in (0, 1))}
+  c_index = {v: len(p_index) + i for i, v in enumerate(sources)}
+  n = len(p_index) + len(c_index)
+  cost = np.zeros(n)
+  for v in sources:
+    cost[c_index[v]] += 1
+    if v in p_index:
+      cost[p_index[v]] -= 1
+  rows, rhs = [], []
+  for src, dsts in dependers.items():
+    for dst in dsts:
+      lo, hi = dependees[dst][src]
+      # P_src <= lo + P_dst
+      row = np.zeros(n)
+      if src in p_index:
+        row[p_index[src]] += 1
+      if dst in p_index:
+        row[p_index[dst]] -= 1
+      rows.append(row)
+      rhs.append(lo)
+      # C_src >= hi + P_dst
+      row = np.zeros(n)
+      row[c_index[src]] -= 1
+      if dst in p_index:
+        row[p_index[dst]] += 1
+      rows.append(row)
+      rhs.append(-hi)
+  result = linprog(cost, A_ub=np.array(rows), b_ub=np.array(rhs),
+                   bounds=[(None, None)] * n, method='highs')
+  if result.status != 0:
+    raise util.InternalError('offset program failed: %s' % result.message)
+  return int(round(result.fun))
+
+
 def find_schedule_native(leaves: Sequence[Leaf],
                          flag: Optional[str] = None) -> Optional[Pattern]:
   """Runs the native scheduler (csrc/soda_cr) over the reference's JSON
@@ -366,14 +504,143 @@ def find_schedule_native(leaves: Sequence[Leaf],
     return merge(left, right, _sub(linearizer.restore(right_offset),
                                    linearizer.restore(offset)))
 
-  tree = build(answer, min(request['rattrs']))
   base = min((idx for idx, _ in leaves), key=_order)
   expected = frozenset((_sub(idx, base), tag) for idx, tag in leaves)
-  if tree.leaves != expected:
+  origin = min(request['rattrs'])
+  candidates = [build(answer, origin)]
+  # --optimal also returns every other tree with as few operations (up to a
+  # cap): the tie is broken by total reuse distance, the second component of
+  # the reference's schedule cost (:398-400)
+  for other in answer.get('alternatives', ()):
+    candidates.append(build(other, origin))
+  if any(tree.leaves != expected for tree in candidates):
     _logger.warning('soda-cr returned a schedule that does not cover the '
                     'operands; falling back to the built-in search')
     return None
-  return tree
+  if flag == '--optimal' and not answer.get('proven_optimal', False):
+    _logger.warning('soda-cr --optimal stopped at its tree budget after %s '
+                    'trees: best schedule found, optimality not proven',
+                    answer.get('trees'))
+  if len(candidates) == 1:
+    return candidates[0]
+  return min(candidates,
+             key=lambda t: (t.num_ops, reference_total_distance(t, linearizer),
+                            str(t)))
+
+
+def find_schedule_exhaustive(leaves: Sequence[Leaf],
+                             limit: int = 8) -> Optional[Pattern]:
+  """Every binary tree over the operands (reference :983-1059,
+  ``CommSchedules.generator``: the first operand stays left, every subset of
+  the rest joins it), cost = (operations, total reuse distance).  Pure
+  Python: only up to ``limit`` operands; the native soda-cr does more."""
+  if len(leaves) > limit:
+    return None
+  dim = len(leaves[0][0])
+  ordered = sorted(leaves, key=lambda leaf: (_order(leaf[0]), leaf[1]))
+  linearizer = Linearizer([idx for idx, _ in leaves])
+
+  def trees(indices: Tuple[int, ...]):
+    if len(indices) == 1:
+      yield leaf_pattern(ordered[indices[0]][1], dim)
+      return
+    rest = indices[1:]
+    for size in range(len(rest)):
+      for chosen in itertools.combinations(rest, size):
+        left = (indices[0],) + chosen
+        right = tuple(i for i in rest if i not in chosen)
+        distance = _sub(ordered[right[0]][0], ordered[left[0]][0])
+        for l in trees(left):
+          for r in trees(right):
+            yield merge(l, r, distance)
+
+  best, best_cost = None, None
+  for tree in trees(tuple(range(len(ordered)))):
+    ops = tree.num_ops
+    if best_cost is not None and ops > best_cost[0]:
+      continue
+    cost = (ops, reference_total_distance(tree, linearizer), str(tree))
+    if best_cost is None or cost < best_cost:
+      best, best_cost = tree, cost
+  return best
+
+
+def _linear_chain(items: Sequence[Item]) -> Item:
+  """Right-deep chain over the items in stream order: i0 + (i1 + (i2 + ...))
+  (reference :1503-1520, ``linear_schedule``).  Returns (base, pattern)."""
+  ordered = sorted(items, key=lambda item: (_order(item[0]), item[1]._hash))
+  base, tree = ordered[-1]
+  for position, pattern in reversed(ordered[:-1]):
+    tree = merge(pattern, tree, _sub(base, position))
+    base = position
+  return base, tree
+
+
+def find_schedule_glore(leaves: Sequence[Leaf]) -> Pattern:
+  """The GLORE heuristic as the reference applies it (reference :1523-1689,
+  ``GloreSchedules``), once along dimension 0 and once along the diagonal:
+
+  1. operands are grouped into lines along the direction;
+  2. inside a line of more than three operands, the stride that pairs the most
+     operands into translates of (operand at the line's end, operand one
+     stride before it) is chosen, and every such pair becomes one shared
+     operand;
+  3. lines that then look alike (same stride, same pairing, same tags) are
+     computed once, as a chain, and reused for every such line;
+  4. what is left is chained in stream order.
+  The direction with fewer operations wins."""
+  dim = len(leaves[0][0])
+  results = []
+  for diagonal in (False, True):
+    lines: Dict[Index, List[Leaf]] = collections.OrderedDict()
+    for idx, tag in leaves:
+      line_id = tuple(x - idx[0] for x in idx[1:]) if diagonal else idx[1:]
+      lines.setdefault(line_id, []).append((idx, tag))
+    by_key: Dict[tuple, List[List[Item]]] = collections.OrderedDict()
+    for line_id, line in lines.items():
+      line.sort(key=lambda leaf: _order(leaf[0]), reverse=True)
+      dists = [line[0][0][0] - idx[0] for idx, _ in line]
+      at = dict(zip(dists, line))
+      chosen = None
+      if len(line) > 3:
+        for stride in range(dists[1], dists[-1]):
+          if stride not in at:
+            continue
+          head = (at[0][1], at[stride][1])
+          pending = list(dists)
+          reused, plain, items = [], [], []
+          while pending:
+            d = pending.pop(0)
+            if d + stride in pending and (at[d][1], at[d + stride][1]) == head:
+              pending.remove(d + stride)
+              reused.append(d)
+              lower, upper = at[d + stride][0], at[d][0]
+              pair = merge(leaf_pattern(at[stride][1], dim),
+                           leaf_pattern(at[0][1], dim), _sub(upper, lower))
+              items.append((lower, pair))
+            else:
+              plain.append(d)
+              items.append((at[d][0], leaf_pattern(at[d][1], dim)))
+          if reused and (chosen is None or
+                         (len(reused), -stride) > (len(chosen[1]), -chosen[0])):
+            chosen = (stride, tuple(reused), tuple(plain), items)
+      if chosen is None:
+        chosen = (0, (), tuple(dists),
+                  [(idx, leaf_pattern(tag, dim)) for idx, tag in line])
+      stride, reused, plain, items = chosen
+      items.sort(key=lambda item: _order(item[0]))
+      shape = tuple((_sub(pos, items[0][0]), pattern) for pos, pattern in items)
+      by_key.setdefault((stride, reused, plain, shape), []).append(items)
+    final: List[Item] = []
+    for (stride, reused, plain, _), groups in by_key.items():
+      if len(groups) > 1 and len(reused) + len(plain) > 1:
+        for items in groups:  # one shared chain, used once per line
+          final.append(_linear_chain(items))
+      else:
+        for items in groups:
+          final.extend(items)
+    results.append(_linear_chain(final)[1] if len(final) > 1 else final[0][1])
+  return min(results, key=lambda tree: (tree.num_ops, str(tree)))
 
 
 def find_schedule(leaves: Sequence[Leaf], beam_width: int = 6,
@@ -390,10 +657,12 @@ def find_schedule(leaves: Sequence[Leaf], beam_width: int = 6,
     beam_width, branch = 2, 2
   # a state is (items, regular): `regular` marks the lineage that only ever
   # followed single-dimension reuse; two such states are always kept so that
-  # the regular decomposition of a grid cannot be crowded out of the beam
-  frontier = [(start, True)]
+  # the regular decomposition of a grid cannot be crowded out of the beam.
+  # The search runs once per preference order of the dimensions for that
+  # single-dimension reuse: the orders reach the same operation count on
+  # regular grids but very different reuse distances (an 11 x 11 box: 220
+  # when rows are summed first, 374 when columns are).
   finished: List[Pattern] = []
-  seen = set()
 
   def rank(state):
     items = state[0]
@@ -402,27 +671,45 @@ def find_schedule(leaves: Sequence[Leaf], beam_width: int = 6,
     return (ops_so_far + len(items) - 1, len(items), sorted(
         (_order(b), p._hash) for b, p in items))
 
-  while frontier:
-    next_frontier = []
-    for items, regular in frontier:
-      moves = _candidate_moves(items, branch)
-      if not moves:
-        finished.append(_finish(items))
-        continue
-      for move in moves:
-        left, right, distance, occurrences, aligned = move[5:]
-        new_items = _apply(items, left, right, distance, occurrences)
-        key = frozenset(collections.Counter(new_items).items())
-        if key in seen:
+  orders = [tuple(reversed(range(dim)))]
+  if dim > 1:
+    orders.append(tuple(range(dim)))
+  for axis_order in orders:
+    frontier = [(start, True)]
+    seen = set()
+    while frontier:
+      next_frontier = []
+      for items, regular in frontier:
+        moves = _candidate_moves(items, branch, axis_order)
+        if not moves:
+          # no sharing left: chain the rest, left-deep and right-deep (same
+          # operations, different reuse distances)
+          finished.append(_finish(items))
+          if len(items) > 2:
+            finished.append(_linear_chain(items)[1])
           continue
-        seen.add(key)
-        next_frontier.append((new_items, regular and aligned))
-    next_frontier.sort(key=rank)
-    keep = next_frontier[:beam_width]
-    protected = [s for s in next_frontier[beam_width:] if s[1]][:2]
-    frontier = keep + protected
-  best = min(finished, key=lambda t: (t.num_ops, total_distance(t), str(t)))
-  return best
+        for move in moves:
+          left, right, distance, occurrences, aligned = move[5:]
+          new_items = _apply(items, left, right, distance, occurrences)
+          key = frozenset(collections.Counter(new_items).items())
+          if key in seen:
+            continue
+          seen.add(key)
+          next_frontier.append((new_items, regular and aligned))
+      next_frontier.sort(key=rank)
+      keep = next_frontier[:beam_width]
+      protected = [s for s in next_frontier[beam_width:] if s[1]][:2]
+      frontier = keep + protected
+  # cost = (operations, total reuse distance) as in the reference (:398-400);
+  # the distance needs an LP per candidate, so only the candidates with the
+  # fewest operations are measured
+  fewest = min(t.num_ops for t in finished)
+  linearizer = Linearizer([idx for idx, _ in leaves])
+  # (Pattern equality is "same leaves": every complete tree is equal to every
+  # other one, so the candidates are told apart by their text)
+  finalists = {str(t): t for t in finished if t.num_ops == fewest}
+  return min(finalists.values(),
+             key=lambda t: (reference_total_distance(t, linearizer), str(t)))
 
 
 # ---------------------------------------------------------------------------
@@ -552,11 +839,29 @@ def computation_reuse(stencil):
       # the method does not ask for the built-in search, else the built-in one
       tree = None
       if not method.startswith('built-in'):
-        flag = {'greedy': '--greedy', 'optimal': '--brute-force',
+        flag = {'greedy': '--greedy', 'optimal': '--optimal',
                 'beam': '--beam'}.get(method)
-        tree = find_schedule_native(expression.leaves, flag)
+        if method == 'glore':
+          tree = find_schedule_glore(expression.leaves)
+        elif method == 'optimal' and len(expression.leaves) > 16:
+          raise util.SemanticError(
+              '--computation-reuse=optimal enumerates every schedule: at most '
+              '16 operands per reduction (this one has %d); use `yes`' %
+              len(expression.leaves))
+        else:
+          tree = find_schedule_native(expression.leaves, flag)
+      elif method.endswith('optimal'):
+        tree = find_schedule_exhaustive(expression.leaves)
+        if tree is None:
+          raise util.SemanticError(
+              '--computation-reuse=built-in:optimal handles at most 8 '
+              'operands per reduction (this one has %d); `optimal` uses the '
+              'native search' % len(expression.leaves))
       if tree is None:
-        tree = find_schedule(expression.leaves)
+        if method == 'optimal':
+          tree = find_schedule_exhaustive(expression.leaves)
+        if tree is None:
+          tree = find_schedule(expression.leaves)
       if tree.num_ops >= len(expression.leaves) - 1:
         return obj  # nothing gained
       _logger.info('%s: %d operations instead of %d: %s', stmt.name,
@@ -590,10 +895,9 @@ def computation_reuse(stencil):
         for other in new_stmts:
           if other.haoda_type is None:
             table.pop(other.name, None)
-        new_stmt.haoda_type = ir.propagate_type(new_stmt.expr,
-                                                new_stmt.symbol_table
-                                                if new_stmt.let else
-                                                table).haoda_type
+        new_stmt.haoda_type = ir.propagate_type(
+            new_stmt.expr, new_stmt.symbol_table if new_stmt.let else table,
+            getattr(stencil, 'float_math', False)).haoda_type
         stencil.invalidate()
         pending.remove(new_stmt)
         progress = True

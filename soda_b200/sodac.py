@@ -59,6 +59,13 @@ def build_parser() -> argparse.ArgumentParser:
                       help='module clustering level (accepted for '
                       'compatibility; the CUDA backend always fuses '
                       'everything)')
+  parser.add_argument('--math-precision', type=str, metavar='(double|float)',
+                      dest='math_precision',
+                      help='how sqrt / fabs / floor / ceil of a float are '
+                      'evaluated: through double (default: what g++ does with '
+                      'the generated code and plain <cmath>) or in float (the '
+                      'std:: float overloads in scope, as Xilinx headers may '
+                      'arrange); applies to every backend and to the oracle')
   parser.add_argument(type=str, dest='soda_src', metavar='file',
                       help='soda source code, - for stdin')
   cuda_backend.add_arguments(parser.add_argument_group('CUDA (B200) backend'))
@@ -111,6 +118,7 @@ def stencil_from_program(program: grammar.SodaProgram,
       tile_size=tile_size,
       unroll_factor=unroll_factor,
       replication_factor=replication_factor,
+      math_precision=get('math_precision'),
       optimizations=opt_args.get_kwargs(args) if args is not None and hasattr(
           args, 'computation_reuse') else {},
   )

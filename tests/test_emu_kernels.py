@@ -146,3 +146,13 @@ def test_one_sided_windows_over_several_passes(text, extent, host_chunks):
                 opts=launcher.make_opts(host_chunks=host_chunks))
   common.assert_matches_oracle(st, extent, outputs,
                                common.oracle_outputs(st, inputs), sentinel=77)
+
+
+@pytest.mark.parametrize('name,kwargs', [
+    ('denoise2d', dict(extent=(100, 30))),
+    ('denoise3d', dict(extent=(60, 19, 7), options={'rows': 8})),
+])
+def test_float_math_mode_under_emulation(name, kwargs):
+  """--math-precision float: sqrtf in the functors, std::sqrt(float) in the
+  oracle; bit-exact through the templates like the default mode."""
+  run_case(name, math_precision='float', **kwargs)

@@ -221,3 +221,11 @@ def test_fast_fp_mode_tolerance():
   inside = common.box_index(st.valid_box('out', extent))
   assert compare.error_count(got[inside], want[inside]) == 0
   assert compare.ulp_distance(got[inside], want[inside]).max() <= 2 * st.iterate
+
+
+@pytest.mark.parametrize('name,extent', [('denoise2d', (500, 300)),
+                                         ('denoise3d', (250, 37, 41))])
+def test_float_math_mode(name, extent):
+  """--math-precision float (sqrt(float) stays float): sqrt.rn.f32 on the GPU
+  is the correctly rounded std::sqrt(float) of the oracle."""
+  run_case(name, extent=extent, seed=31, math_precision='float')

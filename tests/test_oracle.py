@@ -153,3 +153,34 @@ def test_reference_compare_criterion():
   a = np.float32(1.0)
   b = np.nextafter(a, np.float32(2.0))
   assert compare.ulp_distance(np.array([a]), np.array([b]))[0] == 1
+
+
+@pytest.mark.parametrize('name', ['denoise2d', 'denoise3d'])
+def test_math_precision_modes(name):
+  """``sqrt(float)``: through double (default: what g++ makes of the reference's
+  generated code with plain <cmath>) or in float (``--math-precision float``:
+  the std:: float overloads in scope, as Xilinx's headers may arrange).  Both
+  evaluators implement both readings and agree bit for bit in each; the two
+  readings differ from each other (so the switch is not vacuous)."""
+  import numpy as np
+  from oracle import emit_cpp, golden
+  from soda_b200 import ir, sodac
+  results = {}
+  for mode in ('double', 'float'):
+    st = sodac.compile_source(common.source(name), math_precision=mode)
+    g = [s for s in st.local_stmts if s.name == 'g'][0]
+    inner = ir.unwrap(g.expr) if mode == 'float' else g.expr
+    assert (g.expr.haoda_type == ir.FLOAT) and \
+        (isinstance(g.expr, ir.Cast) == (mode == 'double')), inner
+    extent = list(golden.default_extent(st))
+    extent[0] += 9
+    extent[-1] += 7
+    inputs = common.make_inputs(st, extent, seed=17)
+    a = golden.run(st, inputs)['output']
+    b = emit_cpp.Oracle(st).run(inputs)['output']
+    inside = common.box_index(st.valid_box('output', extent))
+    assert np.array_equal(a[inside].view(np.uint32), b[inside].view(np.uint32))
+    results[mode] = a[inside]
+  assert not np.array_equal(results['double'].view(np.uint32),
+                            results['float'].view(np.uint32))
+  assert np.allclose(results['double'], results['float'], rtol=1e-5)

@@ -28,10 +28,14 @@ def cases():
   out = []
   for tb in range(1, 9):
     out.append(('jacobi2d', (16384, 16384), tb, {}))
-  out.append(('jacobi2d', (16384, 16384), 7, {'cells': 8}))
-  out.append(('jacobi2d', (16384, 16384), 8, {'cells': 8}))
-  for tb in range(1, 7):
+  out.append(('jacobi2d', (16384, 16384), 7, {'cells': 4}))
+  out.append(('jacobi2d', (16384, 16384), 8, {'cells': 4}))
+  out.append(('jacobi2d', (16384, 16384), 8, {'chunk': 3}))
+  for tb in range(1, 9):
     out.append(('seidel2d', (16384, 16384), tb, {}))
+  for tb in (4, 5, 6):
+    out.append(('seidel2d', (16384, 16384), tb, {'chunk': 3}))
+    out.append(('seidel2d', (16384, 16384), tb, {'cells': 4}))
   for tb in (1, 2, 3):
     out.append(('blur', (2000, 16384), tb, {}))
     out.append(('blur', (16000, 16384), tb, {}))
