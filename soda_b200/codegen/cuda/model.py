@@ -60,6 +60,7 @@ ISSUE_EFF_LOW_OCCUPANCY = 0.67   # fewer than three warps per scheduler
 ISSUE_EFF_3D = {True: 0.80, False: 0.60}   # keyed by (warps per CTA <= 4)
 LAUNCH_SECONDS = 8e-6            # per pass: launch latency, ramp-up, tail
 NORM = 3.0
+NEAR_TIE = 0.12  # choose_time_block: how much throughput a smaller block may cost
 REGISTER_FILE = 65536
 # thread-instructions per lane and step that do not depend on the program:
 # input vector load from the TMA ring, store, pointer bumps, barrier / mbarrier
@@ -271,17 +272,26 @@ DEFAULT_EXTENT = {2: (16384, 16384), 3: (512, 512, 512)}
 def choose_time_block(stencil, options: Optional[Dict] = None,
                       extent: Optional[List[int]] = None,
                       limit: int = 12) -> int:
-  """The time block with the highest modelled throughput; ties and near-ties
-  (within 3 %) go to the smaller one (shorter halos, shorter warm-up).
+  """The smallest time block whose modelled throughput is within 12 % of the
+  best one.  Fusing more iterations than that buys little and costs halo
+  (narrow grids, multi-GPU ghosts), warm-up slices per segment and registers
+  (jacobi2d at time block 8 uses 252 of 255), and it moves the pass from the
+  HBM side of the roofline to the FMA pipe, where a pass no longer streams at
+  the memory system's speed: measured on B200, jacobi2d 16384^2 runs 4065
+  Gcell-updates/s at 0.83 of the HBM roofline with time block 6 and 4442 at
+  0.68 with time block 8 (profiles/r02_time_block_sweep.jsonl);
+  ``--cuda-time-block 8`` asks for the latter.
   ``extent`` (or ``options['extent_hint']``) is the grid the library will
   mostly run on; the program itself does not fix one."""
   extent = extent or (options or {}).get('extent_hint') or \
       DEFAULT_EXTENT.get(stencil.dim)
-  best_tb, best = 1, None
+  estimates = {}
   for tb in range(1, min(stencil.iterate, limit) + 1):
     est = estimate(stencil, tb, options, extent)
-    if est is None:
-      continue
-    if best is None or est['gcells'] > best * 1.03:
-      best_tb, best = tb, est['gcells']
-  return best_tb
+    if est is not None:
+      estimates[tb] = est['gcells']
+  if not estimates:
+    return 1
+  best = max(estimates.values())
+  return min(tb for tb, gcells in estimates.items()
+             if gcells >= (1.0 - NEAR_TIE) * best)

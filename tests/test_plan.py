@@ -78,9 +78,9 @@ def test_pass_schedule_and_time_block_choice():
   assert plan.choose_time_block(common.stencil('denoise2d')) == 1
   assert plan.choose_time_block(common.stencil('jacobi2d')) == 2
   # the throughput model's choices (model.py; validated on B200 in
-  # tests/test_model.py): 8 fused iterations while 8-cell lanes of packed
-  # pairs fit the register file in 2-D, issue-bound beyond 2 in 3-D
-  assert plan.choose_time_block(common.stencil('jacobi2d', iterate=64)) == 8
+  # tests/test_model.py): the smallest time block within 12 % of the best -
+  # 6 fused iterations in 2-D (8 is 9 % faster but FMA-bound), 2 in 3-D
+  assert plan.choose_time_block(common.stencil('jacobi2d', iterate=64)) == 6
   assert plan.choose_time_block(common.stencil('heat3d', iterate=32)) == 2
   assert plan.choose_time_block(common.stencil('jacobi3d', iterate=32)) == 2
   assert plan.choose_time_block(common.stencil('heat3d', iterate=32), 3) == 3
