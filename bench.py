@@ -68,6 +68,9 @@ CONFIGS = {
     'C5_jacobi2d': dict(program='jacobi2d', overrides={'iterate': 256},
                         extent=(65536, 65536)),
 }
+# halo transport of the slab runtime at N > 1: 'nccl' = the library's own NCCL
+# communicator (default), 'torch' = torch.distributed point-to-point callbacks
+TRANSPORT = os.environ.get('SODA_BENCH_TRANSPORT', 'nccl')
 HEADLINE = 'C2_jacobi2d'
 OTHER = ('C1_blur', 'C2_jacobi2d_tb8', 'C3_heat3d', 'C3_jacobi3d', 'C4_denoise3d',
          'C4_denoise3d_cr', 'C4_denoise3d_float_math')
@@ -530,7 +533,10 @@ def run_ours(args, out):
   torch.cuda.set_device(local_rank)
   device = torch.device('cuda', local_rank)
   if world > 1:
-    dist.init_process_group('nccl', device_id=device)
+    import datetime
+    # a rank that fails must not leave the others waiting for ten minutes
+    dist.init_process_group('nccl', device_id=device,
+                            timeout=datetime.timedelta(seconds=180))
 
   st, prog = config_program(HEADLINE)
   stream = torch.cuda.current_stream().cuda_stream
@@ -587,7 +593,7 @@ def run_ours(args, out):
   else:
     runner = multi_gpu.SlabRunner(prog, global_extent, device,
                                   rank=rank, world=world,
-                                  stream_handle=stream)
+                                  stream_handle=stream, transport=TRANSPORT)
     lo, hi = runner.own
     fill_synthetic(runner.inputs[0][lo:hi], runner.begin, 0, WIDTH)
     step = runner.run
@@ -693,7 +699,7 @@ def run_ours(args, out):
     torch.cuda.empty_cache()
     host_runner = multi_gpu.SlabRunner(prog, global_extent, device, rank=rank,
                                        world=world, stream_handle=stream,
-                                       exchange_every=-1)
+                                       exchange_every=-1, transport=TRANSPORT)
     rows = host_runner.end - host_runner.begin
     pinned_in = launcher.HostBuffer(prog, (rows, WIDTH), np.float32, local_rank)
     pinned_out = launcher.HostBuffer(prog, (rows, WIDTH), np.float32,
@@ -872,7 +878,8 @@ def run_c5_strong(args, device, stream, rank, world, peak, barrier,
     groups = 1
   else:
     runner = multi_gpu.SlabRunner(prog, (width, height), device, rank=rank,
-                                  world=world, stream_handle=stream)
+                                  world=world, stream_handle=stream,
+                                  transport=TRANSPORT)
     lo, hi = runner.own
     fill_synthetic(runner.inputs[0][lo:hi], runner.begin, 0, width)
     step = runner.run
