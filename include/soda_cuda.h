@@ -126,6 +126,12 @@ typedef struct soda_cuda_program_info {
   const char* param_names[SODA_CUDA_MAX_TENSORS];
   int32_t param_dtypes[SODA_CUDA_MAX_TENSORS];
   int32_t param_elems[SODA_CUDA_MAX_TENSORS];   /* product of the declared sizes */
+  /* Dimensions of the program as written.  1 for a 1-D program, which runs as
+   * the 2-D program over an N x 1 grid (`dim` == 2: lanes along the only
+   * dimension, one slice in the streamed one).  soda_cuda_<app> takes the 1-D
+   * quadruples of the source program; the generic entry points take the 2-D
+   * extent {N, 1} and strides {1, N}. */
+  int32_t source_dim;
 } soda_cuda_program_info;
 
 typedef struct soda_cuda_plan soda_cuda_plan;   /* opaque */

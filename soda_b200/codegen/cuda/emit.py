@@ -309,6 +309,11 @@ def emit_program(stencil,
   options = dict(options or {})
   # integer widths C++ does not have become containers + explicit wraps
   stencil = widths.lower(stencil)
+  source_dim = stencil.dim
+  if stencil.dim == 1:
+    # a 1-D program runs as the 2-D program over an N x 1 grid
+    from soda_b200.optimization import lift
+    stencil = lift.lift_1d(stencil)
   dim = stencil.dim
   for what, stmts in (('inputs', stencil.input_stmts),
                       ('outputs', stencil.output_stmts),
@@ -411,6 +416,7 @@ def emit_program(stencil,
                (0 if options.get('fast_fp') else 1))
   lines.append('    d.info.algorithmic_bytes_per_cell_per_pass = %d;' %
                bytes_per_cell)
+  lines.append('    d.info.source_dim = %d;' % source_dim)
   lines.append('    d.info.num_params = %d;' % len(stencil.param_stmts))
   for k, stmt in enumerate(stencil.param_stmts):
     elems = 1
@@ -459,9 +465,19 @@ def emit_program(stencil,
   lines.append('  if (var_%s_extent == nullptr)' % first)
   lines.append('    return soda::rt::fail(SODA_CUDA_BAD_ARGUMENT, '
                '"extent is NULL");')
+  if source_dim == 1:
+    # the caller's quadruples are 1-D (the program as written): N cells,
+    # stride 1; the library runs the N x 1 grid
+    lines.append('  const int32_t soda_extent[2] = {var_%s_extent[0], 1};' % first)
+    lines.append('  const int32_t soda_stride[2] = {1, var_%s_extent[0]};' % first)
+    for stmt in stencil.input_stmts + stencil.output_stmts:
+      lines.append('  if (var_%s_stride != nullptr && var_%s_stride[0] != 1)' %
+                   (stmt.name, stmt.name))
+      lines.append('    return soda::rt::fail(SODA_CUDA_UNSUPPORTED, '
+                   '"1-D arrays must be dense");')
   for stmt in stencil.input_stmts[1:] + stencil.output_stmts:
     lines.append('  if (var_%s_extent != nullptr)' % stmt.name)
-    lines.append('    for (int d = 0; d < %d; ++d)' % dim)
+    lines.append('    for (int d = 0; d < %d; ++d)' % source_dim)
     lines.append('      if (var_%s_extent[d] != var_%s_extent[d])' %
                  (stmt.name, first))
     lines.append('        return soda::rt::fail(SODA_CUDA_BAD_ARGUMENT, '
@@ -476,12 +492,14 @@ def emit_program(stencil,
                  'if (status != SODA_CUDA_OK) return status; }' % (k, stmt.name))
   lines.append('  const void* in_ptrs[] = {%s};' %
                ', '.join('var_%s_ptr' % s.name for s in stencil.input_stmts))
+  stride_of = (lambda s: 'soda_stride') if source_dim == 1 else (
+      lambda s: 'var_%s_stride' % s.name)
   lines.append('  const int32_t* in_strides[] = {%s};' %
-               ', '.join('var_%s_stride' % s.name for s in stencil.input_stmts))
+               ', '.join(stride_of(s) for s in stencil.input_stmts))
   lines.append('  void* out_ptrs[] = {%s};' %
                ', '.join('var_%s_ptr' % s.name for s in stencil.output_stmts))
   lines.append('  const int32_t* out_strides[] = {%s};' % ', '.join(
-      'var_%s_stride' % s.name for s in stencil.output_stmts))
+      stride_of(s) for s in stencil.output_stmts))
   gpus = int(options.get('gpus') or 0)
   if gpus > 1:
     # sodac --cuda-gpus N: the default of this library, unless the caller's
@@ -495,6 +513,7 @@ def emit_program(stencil,
                  % gpus)
     lines.append('  opts = &soda_opts;')
   lines.append('  return soda_cuda_run_host(in_ptrs, in_strides, out_ptrs, '
-               'out_strides, var_%s_extent, opts);' % first)
+               'out_strides, %s, opts);' %
+               ('soda_extent' if source_dim == 1 else 'var_%s_extent' % first))
   lines.append('}')
   return '\n'.join(lines) + '\n'

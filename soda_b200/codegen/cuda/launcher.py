@@ -98,6 +98,7 @@ class ProgramInfo(ctypes.Structure):
       ('param_names', ctypes.c_char_p * MAX_TENSORS),
       ('param_dtypes', ctypes.c_int32 * MAX_TENSORS),
       ('param_elems', ctypes.c_int32 * MAX_TENSORS),
+      ('source_dim', ctypes.c_int32),
   ]
 
 
@@ -141,6 +142,8 @@ class CudaProgram:
     self.app_name = info.app_name.decode()
     self.soda_source = info.soda_source.decode()
     self.dim = info.dim
+    # a 1-D program runs lifted to an N x 1 grid (include/soda_cuda.h)
+    self.source_dim = info.source_dim or info.dim
     self.iterate = info.iterate
     self.input_names = [info.input_names[i].decode()
                         for i in range(info.num_inputs)]
@@ -178,6 +181,12 @@ class CudaProgram:
     return [(self.info.final_lo[output][d],
              extent[d] - self.info.final_hi[output][d])
             for d in range(self.dim)]
+
+  def _lifted(self, array: np.ndarray) -> np.ndarray:
+    """1-D arrays of a 1-D program as the N x 1 grid the library runs."""
+    if self.source_dim == 1 and array.ndim == 1:
+      return array.reshape(1, -1)
+    return array
 
   def _extent_of(self, array: np.ndarray):
     if array.ndim != self.dim:
@@ -225,9 +234,10 @@ class CudaProgram:
     if self.param_names and params is None and use_app_entry:
       raise ValueError('program %s needs params %s' %
                        (self.app_name, self.param_names))
+    flat = self.source_dim == 1 and inputs[self.input_names[0]].ndim == 1
     ins = []
     for name, dtype in zip(self.input_names, self.input_dtypes):
-      array = inputs[name]
+      array = self._lifted(inputs[name])
       if array.dtype != dtype:
         raise TypeError('input %s must be %s, got %s' %
                         (name, dtype, array.dtype))
@@ -235,12 +245,13 @@ class CudaProgram:
     extent = self._extent_of(ins[0])
     if outputs is None:
       outputs = {
-          name: np.zeros(extent[::-1], dtype=dtype)
+          name: np.zeros(extent[::-1][1:] if flat else extent[::-1],
+                         dtype=dtype)
           for name, dtype in zip(self.output_names, self.output_dtypes)
       }
     outs = []
     for name, dtype in zip(self.output_names, self.output_dtypes):
-      array = outputs[name]
+      array = self._lifted(outputs[name])
       if array.dtype != dtype or self._extent_of(array) != extent:
         raise TypeError('output %s must be %s of extent %s' %
                         (name, dtype, extent))
@@ -256,10 +267,15 @@ class CudaProgram:
                for a in ins + outs]
     opts_ref = ctypes.byref(opts) if opts is not None else None
     if use_app_entry:
-      # the program-named entry point: (ptr, extent, stride, min) per tensor
+      # the program-named entry point: (ptr, extent, stride, min) per tensor,
+      # in the dimensions of the program as written
       args = []
+      n = self.source_dim
       for array, stride in zip(ins + outs, strides):
-        args += [ctypes.c_void_p(array.ctypes.data), c_extent, stride, zeros]
+        args += [ctypes.c_void_p(array.ctypes.data),
+                 (ctypes.c_int32 * n)(*extent[:n]),
+                 (ctypes.c_int32 * n)(*list(stride)[:n]),
+                 (ctypes.c_int32 * n)(*([0] * n))]
       keep = []
       for index, name in enumerate(self.param_names):
         array = self._param_array(index, params[name])

@@ -242,7 +242,9 @@ def make_pass_plan(stencil,
   dim = stencil.dim
   if dim not in (2, 3):
     raise util.SemanticError(
-        'the CUDA backend supports 2-D and 3-D programs, got %d-D' % dim)
+        'the CUDA kernel templates take 2-D and 3-D programs, got %d-D '
+        '(1-D programs are lifted to N x 1 by emit_program; 4-D ones are not '
+        'supported)' % dim)
   if time_block < 1:
     raise util.SemanticError('time block must be positive')
   if time_block > 1 and len(stencil.input_stmts) != len(stencil.output_stmts):

@@ -177,3 +177,28 @@ def test_several_warp_ctas_on_a_small_grid():
   result = subprocess.run([sys.executable, '-c', code], cwd=common.ROOT,
                           env=env, capture_output=True, text=True, timeout=900)
   assert result.returncode == 0 and 'ok' in result.stdout, result.stderr[-2000:]
+
+
+def test_one_dimensional_program_under_emulation():
+  """A 1-D program runs lifted to an N x 1 grid (optimization/lift.py): same
+  values and valid range as the 1-D golden loops, through the program-named
+  entry point with 1-D quadruples and through the generic 2-D one."""
+  import os
+  from soda_b200 import sodac
+  with open(os.path.join(common.ROOT, 'tests', 'src_extra',
+                         'smooth1d.soda')) as fp:
+    st = sodac.compile_source(fp.read())
+  assert st.dim == 1
+  prog = launcher.CudaProgram(build_emu.build_emu_library(st, time_block=2))
+  assert (prog.dim, prog.source_dim, prog.num_passes) == (2, 1, 2)
+  for n in (700, 5, 7):
+    x = np.random.default_rng(n).random((n,), dtype=np.float32)
+    want = common.oracle_outputs(st, {'a': x})['b']
+    (lo, hi), = st.valid_box('b', (n,))
+    for app_entry in (True, False):
+      out = np.full((n,), 77, dtype=np.float32)
+      prog.run_host({'a': x}, {'b': out}, use_app_entry=app_entry)
+      if hi > lo:
+        assert np.array_equal(out[lo:hi].view(np.uint32),
+                              want[lo:hi].view(np.uint32))
+      assert np.all(out[:max(lo, 0)] == 77) and np.all(out[max(hi, lo):] == 77)

@@ -229,3 +229,25 @@ def test_float_math_mode(name, extent):
   """--math-precision float (sqrt(float) stays float): sqrt.rn.f32 on the GPU
   is the correctly rounded std::sqrt(float) of the oracle."""
   run_case(name, extent=extent, seed=31, math_precision='float')
+
+
+def test_one_dimensional_program():
+  """tests/src_extra/smooth1d.soda: a 1-D program runs lifted to N x 1
+  (optimization/lift.py); bit-exact against the 1-D golden loops."""
+  import os
+  from soda_b200 import sodac
+  with open(os.path.join(common.ROOT, 'tests', 'src_extra',
+                         'smooth1d.soda')) as fp:
+    st = sodac.compile_source(fp.read())
+  prog = cuda_backend.compile_stencil(st)
+  assert (prog.dim, prog.source_dim) == (2, 1)
+  for n in (1000003, 100, 6):
+    x = np.random.default_rng(n).random((n,), dtype=np.float32)
+    want = common.oracle_outputs(st, {'a': x})['b']
+    out = np.full((n,), 77, dtype=np.float32)
+    prog.run_host({'a': x}, {'b': out})
+    (lo, hi), = st.valid_box('b', (n,))
+    if hi > lo:
+      assert np.array_equal(out[lo:hi].view(np.uint32),
+                            want[lo:hi].view(np.uint32))
+    assert np.all(out[:lo] == 77) and np.all(out[max(hi, lo):] == 77)
