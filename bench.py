@@ -258,6 +258,52 @@ def cpu_baseline(sample_iterate=4, repeats=2):
   }
 
 
+DATAFLOW_SAMPLE = dict(tile=2048, rows=1024, iterate=8)
+
+
+def dataflow_stencil():
+  """The headline program as the reference's FPGA flow would see a bounded
+  sample of it: one 2048-wide tile, unroll factor 2, 8 iterations."""
+  return config_stencil(HEADLINE, iterate=DATAFLOW_SAMPLE['iterate'],
+                        tile_size=[DATAFLOW_SAMPLE['tile']], unroll_factor=2)
+
+
+def cpu_baseline_dataflow():
+  """Second CPU baseline: the reference-style
+  dataflow kernel - modules, FIFOs, delay lines, burst words, printed by
+  oracle/dataflow_kernel.py - under C-simulation semantics (modules run one
+  after the other over unbounded streams, single-threaded by construction)."""
+  import numpy as np
+  from oracle import dataflow_kernel
+  from soda_b200.codegen.cuda import stream_layout
+  st = dataflow_stencil()
+  extent = (DATAFLOW_SAMPLE['tile'], DATAFLOW_SAMPLE['rows'])
+  kernel = dataflow_kernel.DataflowKernel(st, timed=True)
+  layout = stream_layout.TensorLayout(st, st.input_names[0], extent)
+  cycles = dataflow_kernel.cycle_count(st, extent)
+  rng = np.random.default_rng(2)
+  in_banks = {st.input_names[0]: [rng.random(layout.elems_per_bank,
+                                             dtype=np.float32)]}
+  out_banks = {st.output_names[0]: [np.zeros(layout.elems_per_bank,
+                                             dtype=np.float32)]}
+  t0 = time.perf_counter()
+  kernel.run(in_banks, out_banks, cycles)
+  seconds = time.perf_counter() - t0
+  counts = dataflow_kernel.summary(st)
+  return {
+      'value': extent[0] * extent[1] * st.iterate / seconds / 1e9,
+      'unit': 'Gcell-updates/s',
+      'cores': 1,
+      'kind': 'port (reference-style dataflow kernel, C simulation)',
+      'sample': '%dx%d grid as one tile, %d of %d iterations, unroll factor 2, '
+                'kernel only (streams already tiled), g++ -O3 -march=native' %
+                (extent[0], extent[1], st.iterate, ITERATE),
+      'modules': {k: counts[k] for k in ('load', 'forward', 'compute', 'store')},
+      'fifos': counts['fifos'],
+      'seconds': seconds,
+  }
+
+
 def workload_config(n_gpus, time_block=None, passes=None):
   return {
       'workload': 'jacobi2d fp32 5-point %dx%d iterate %d' %
@@ -845,6 +891,11 @@ def run_ours(args, out):
     }
     if world == 1 and not args.no_cpu_baseline:
       line['cpu_baseline'] = cpu_baseline()
+      try:
+        line['cpu_baseline_dataflow'] = cpu_baseline_dataflow()
+      except Exception as e:  # pylint: disable=broad-except
+        line['cpu_baseline_dataflow'] = {
+            'error': '%s: %s' % (type(e).__name__, e)}
     out.emit(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
