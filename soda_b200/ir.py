@@ -33,10 +33,14 @@ _STD_INT_WIDTHS = (8, 16, 32, 64)
 class Type:
   """A SODA element type such as ``uint16``, ``int32``, ``float``, ``double``.
 
-  Arbitrary widths (``uint6``, ``int27``, ``float18_3``) parse and print, but
-  only the widths C++ has (<cstdint> integers, float, double) and IEEE ``half``
-  can be executed by the CUDA backend and the oracle; ``c_type`` raises for
-  the others.
+  Arbitrary widths (``uint6``, ``int27``, ``float18_3``) parse and print.  The
+  widths C++ has (<cstdint> integers, float, double) and IEEE ``half`` execute
+  as such; other integers of up to 63 bits are lowered to containers
+  (``is_lowerable``); ``c_type`` raises for what remains: fixed-point types
+  (the reference prints ``ap_fixed<N, M>``, whose arithmetic lives in the
+  Xilinx headers and which no reference test executes - nothing to pin a
+  restatement against) and custom floats (which the reference cannot print as
+  C either).
   """
   __slots__ = ('_name',)
 
@@ -105,20 +109,27 @@ class Type:
 
   @property
   def is_lowerable(self) -> bool:
-    """An integer of 1..31 bits that C++ does not have: stored in the next
+    """An integer of 1..63 bits that C++ does not have: stored in the next
     <cstdint> container and wrapped to its width on every store
     (soda_b200/optimization/widths.py)."""
     m = _TYPE_RE.match(self._name)
     return bool(m and m.group(1) != 'float' and m.group(3) is None and
                 int(m.group(2)) not in _STD_INT_WIDTHS and
-                1 <= int(m.group(2)) <= 31)
+                1 <= int(m.group(2)) <= 63)
 
   @property
   def container(self) -> 'Type':
-    """The <cstdint> type that stores a value of this type."""
+    """The <cstdint> type that stores a value of this type.  33..63-bit values,
+    signed or not, live in an ``int64``: it holds every such value, and the
+    arithmetic on what is loaded from it is then signed 64-bit - the widening
+    arithmetic of ``ap_int`` as long as intermediates fit 63 bits (an
+    ``ap_uint<40>`` occupies 8 bytes with the value zero-extended, so the bytes
+    are those of the reference's array)."""
     if not self.is_lowerable:
       return self
     bits = self.width_in_bits
+    if bits > 32:
+      return Type('int64')
     width = 8 if bits <= 8 else 16 if bits <= 16 else 32
     return Type('%s%d' % ('int' if self.is_signed else 'uint', width))
 
@@ -171,6 +182,8 @@ def _promote(t: Type) -> Type:
     return t
   if t == 'bool' or t.width_in_bits < 32:
     return INT32
+  if t.is_lowerable:
+    return INT64  # 33..63 bits: see Type.container
   return t
 
 

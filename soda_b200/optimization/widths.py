@@ -8,7 +8,8 @@ is exact (``ap_int`` operators widen their result).  This pass rewrites a
 program that uses such types into one that only uses <cstdint> types:
 
 * every tensor / let / cast of type ``uintN`` (``intN``) becomes the smallest
-  standard container type (``uint8``, ``uint16``, ``uint32``; ``int8`` ...);
+  standard container type (``uint8``, ``uint16``, ``uint32``; ``int8`` ...;
+  ``int64`` for every width of 33..63 bits, ``ir.Type.container``);
 * every value stored into it is wrapped explicitly, in the DSL itself:
   ``(e) & (2^N - 1)`` for ``uintN``, ``(((e) & (2^N - 1)) ^ 2^(N-1)) - 2^(N-1)``
   for ``intN``;
@@ -16,9 +17,12 @@ program that uses such types into one that only uses <cstdint> types:
   hold N-bit values; a caller's container array could hold more).
 
 Exactness of the arithmetic in between is the same contract as for the
-standard narrow types: intermediates must fit in 32 bits,
-where C++ ``int`` arithmetic and the widening ``ap_int`` arithmetic agree.
-Widths above 31 bits and fixed-point / custom float types stay unsupported.
+standard narrow types: intermediates must fit in 32 bits
+(63 bits once a 33..63-bit value takes part: those are loaded as ``int64``),
+where C++ arithmetic and the widening ``ap_int`` arithmetic agree.
+Fixed-point (``uint18_3``) and custom float types stay unsupported: the former
+would be ``ap_fixed`` arithmetic from the Xilinx headers, which no reference
+test executes; the reference has no C type at all for the latter.
 
 The oracle does not use this pass: oracle/golden.py and oracle/emit_cpp.py
 wrap natively, so that a mistake here cannot hide.
@@ -140,6 +144,6 @@ def lower(stencil):
             list(stencil.local_types) + list(stencil.param_types)):
     if not t.is_executable and not t.is_lowerable:
       raise util.SemanticError(
-          'type %s is not supported by the CUDA backend (integers up to 31 '
-          'bits, the <cstdint> types, float and double are)' % t)
+          'type %s is not supported by the CUDA backend (integers up to 64 '
+          'bits, half, float and double are)' % t)
   return sodac.compile_source(lower_text(str(stencil)))

@@ -118,11 +118,11 @@ def test_narrow_widths_are_lowered_to_containers_and_wraps():
   # programs without such types pass through untouched
   plain = common.stencil('blur')
   assert widths.lower(plain) is plain
-  # 40-bit integers and custom floats stay unsupported
+  # custom floats stay unsupported (the reference has no C type for them)
   with pytest.raises(util.SemanticError):
     emit.emit_program(sodac.compile_source(
         open(os.path.join(EXTRA, 'narrow2d.soda')).read().replace(
-            'uint10', 'uint40')))
+            'uint10', 'float18_3')))
 
 
 def _narrow_inputs(st, extent, seed=9):
@@ -166,6 +166,59 @@ def test_narrow_widths_on_gpu():
   prog = cuda_backend.compile_stencil(st, time_block=2)
   inputs = _narrow_inputs(st, extent)
   outputs = {'b': np.full(extent[::-1], 77, dtype=np.uint8)}
+  prog.run_host(inputs, outputs)
+  common.assert_matches_oracle(st, extent, outputs,
+                               emit_cpp.Oracle(st).run(inputs), sentinel=77)
+
+
+# ---- 33..63-bit integers: int64 containers ------------------------------------
+
+def _wide_inputs(extent, seed=10):
+  rng = np.random.default_rng(seed)
+  # garbage above bit 39: an ap_uint<40> array cannot hold it
+  return {'a': rng.integers(0, 2**62, extent[::-1]).astype(np.int64)}
+
+
+def test_wide_widths_oracles_and_lowering_agree():
+  from soda_b200.optimization import widths
+  st = stencil('wide2d')
+  low = widths.lower(st)
+  assert not widths.has_narrow_types(low)
+  assert [str(t) for t in low.input_types + low.output_types +
+          tuple(low.local_types)] == ['int64'] * 4
+  extent = (70, 19)
+  inputs = _wide_inputs(extent)
+  a = golden.run(st, inputs)
+  b = emit_cpp.Oracle(st).run(inputs)
+  c = golden.run(low, inputs)
+  index = common.box_index(st.valid_box('b', extent))
+  assert np.array_equal(a['b'][index], b['b'][index])
+  assert np.array_equal(a['b'][index], c['b'][index])
+  assert 2**39 < a['b'][index].max() < 2**40 and a['b'][index].min() >= 0
+  assert len(np.unique(a['b'][index])) > 500
+
+
+def test_wide_widths_under_emulation():
+  st = stencil('wide2d')
+  extent = (90, 21)
+  prog = launcher.CudaProgram(build_emu.build_emu_library(st))
+  assert [str(d) for d in prog.input_dtypes + prog.output_dtypes] == ['int64',
+                                                                      'int64']
+  inputs = _wide_inputs(extent)
+  outputs = {'b': np.full(extent[::-1], 77, dtype=np.int64)}
+  prog.run_host(inputs, outputs)
+  common.assert_matches_oracle(st, extent, outputs,
+                               emit_cpp.Oracle(st).run(inputs), sentinel=77)
+
+
+@pytest.mark.gpu
+def test_wide_widths_on_gpu():
+  from soda_b200.codegen import cuda as cuda_backend
+  st = stencil('wide2d')
+  extent = (1000, 211)
+  prog = cuda_backend.compile_stencil(st)
+  inputs = _wide_inputs(extent)
+  outputs = {'b': np.full(extent[::-1], 77, dtype=np.int64)}
   prog.run_host(inputs, outputs)
   common.assert_matches_oracle(st, extent, outputs,
                                emit_cpp.Oracle(st).run(inputs), sentinel=77)
