@@ -883,6 +883,15 @@ struct HostPipeline {
     return SODA_CUDA_OK;
   }
 
+  // SODA_CUDA_HOST_RAMP=0 keeps equal chunks (A/B measurements)
+  static bool host_ramp_enabled() {
+    static const bool enabled = [] {
+      const char* env = getenv("SODA_CUDA_HOST_RAMP");
+      return env == nullptr || env[0] != '0';
+    }();
+    return enabled;
+  }
+
   static int choose_chunks(const ProgramDesc& prog, const soda_cuda_plan* plan,
                            int slices) {
     int reach_lo = 0, reach_hi = 0;
@@ -894,7 +903,9 @@ struct HostPipeline {
     for (int i = 0; i < prog.info.num_inputs; ++i)
       bytes += slice_cells * slices * prog.in_elem_bytes[i];
     int chunks = plan->host_chunks;
-    if (chunks <= 0) {
+    if (chunks < 0) {
+      chunks = -chunks;  // this many chunks, shorter at both ends (see issue())
+    } else if (chunks == 0) {
       chunks = 1;
       if (bytes >= (32LL << 20)) {
         // chunks of at least 8x the reach: at most 12.5 % redundant compute at
@@ -967,11 +978,36 @@ struct HostPipeline {
       if (status != SODA_CUDA_OK) return status;
     }
 
-    // upload pieces: the chunk bounds, stretched to what the host holds
+    // chunk bounds.  While the first chunk is uploaded nothing else can run,
+    // and nothing overlaps the download of the last one: when the chunk count
+    // is the pipeline's own choice, the chunks at both ends are shorter (a
+    // quarter, then half of an inner chunk), which cuts those two exposed
+    // copies to a quarter at the price of some redundant seam compute in four
+    // small chunks.  An explicit count (opts) keeps equal chunks.
     std::vector<int> bound(chunks + 1), piece(chunks + 1);
+    const bool ramp = plan->host_chunks <= 0 && chunks >= 8 && host_ramp_enabled();
+    if (ramp) {
+      // weights 1/4, 1/2, 1 ... 1, 1/2, 1/4 in quarter units
+      std::vector<int> weight(chunks, 4);
+      weight[0] = weight[chunks - 1] = 1;
+      weight[1] = weight[chunks - 2] = 2;
+      long long total = 0, run = 0;
+      for (int w : weight) total += w;
+      bound[0] = own_lo;
+      for (int k = 0; k < chunks; ++k) {
+        run += weight[k];
+        bound[k + 1] = own_lo + static_cast<int>(slices * run / total);
+      }
+    } else {
+      for (int k = 0; k <= chunks; ++k)
+        bound[k] = own_lo + static_cast<int>(static_cast<long long>(slices) * k / chunks);
+    }
+    // upload pieces: piece k ends where the window of chunk k ends (its upper
+    // bound plus the reach of all passes), so that chunk k waits for its own
+    // piece only, not for the whole upload of chunk k + 1; stretched to what
+    // the host holds at both ends
     for (int k = 0; k <= chunks; ++k)
-      bound[k] = own_lo + static_cast<int>(static_cast<long long>(slices) * k / chunks);
-    piece = bound;
+      piece[k] = std::min(host_hi, std::max(host_lo, bound[k] + reach_hi));
     piece[0] = host_lo;
     piece[chunks] = host_hi;
     std::vector<cudaEvent_t> copied(chunks), computed(chunks);

@@ -99,6 +99,19 @@ def test_pipelined_host_path_under_emulation(name, kwargs):
   run_case(name, host_chunks=3, **kwargs)
 
 
+@pytest.mark.parametrize('name,kwargs', [
+    ('jacobi2d', dict(extent=(70, 200), time_block=2, iterate=5)),
+    ('heat3d', dict(extent=(40, 12, 90), time_block=2, iterate=4,
+                    options={'rows': 8})),
+    ('blur', dict(extent=(80, 33), iterate=2)),  # ramped chunks of 1-2 rows
+])
+def test_ramped_host_chunks_under_emulation(name, kwargs):
+  """A negative chunk count selects what the pipeline chooses by itself for
+  large grids: shorter chunks at both ends, upload pieces that end where the
+  chunk windows end."""
+  run_case(name, host_chunks=-8, **kwargs)
+
+
 ONE_SIDED_2D_NEG = '''kernel: one_sided_neg
 burst width: 64
 unroll factor: 2
