@@ -84,8 +84,9 @@ typedef struct soda_cuda_opts {
   int32_t reserved[5];   /* reserved[0]: chunks of the pipelined host path (copy/compute
                           * overlap of soda_cuda_plan_run_host); 0 = auto, 1 = off,
                           * n > 1: n equal chunks, -n: n chunks of which the two at
-                          * each end are a quarter and a half as long (what auto does
-                          * for large grids: less exposed copy time at both ends)
+                          * each end are a quarter and a half as long (less exposed
+                          * copy time at both ends, smaller launches; auto uses equal
+                          * chunks, which measured faster on B200)
                           * reserved[1]: soda_cuda_<app> / soda_cuda_run_host split the
                           * grid over this many devices (0 .. n-1) when > 1
                           * (sodac --cuda-gpus; see soda_cuda_multi_run_host) */

@@ -84,6 +84,48 @@ def _as(value, t: ir.Type):
     return arr.astype(dtype)
 
 
+def _raw(value, t: ir.Type):
+  """(scaled int64 integers, fractional bits) of a fixed-point or integer
+  value."""
+  if t is not None and t.is_float:
+    raise TypeError('fixed-point arithmetic mixed with a floating-point value; '
+                    'cast one side explicitly')
+  return np.asarray(value).astype(np.int64), (t.frac_bits if t is not None
+                                               else 0)
+
+
+def _convert(value, source: ir.Type, t: ir.Type):
+  """Conversion of ``value`` of type ``source`` to ``t`` where one of them is a
+  fixed-point type (``ap_fixed`` defaults: AP_TRN, AP_WRAP; restated from the
+  public documentation, see soda_b200/optimization/fixed_point.py - which this
+  evaluator deliberately does not use)."""
+  if t.is_fixed:
+    frac = t.frac_bits
+    if source is not None and source.is_float:
+      with np.errstate(invalid='ignore'):
+        raw = np.floor(np.asarray(value).astype(np.float64) *
+                       float(1 << frac)).astype(np.int64)
+    else:
+      raw, have = _raw(value, source)
+      if have >= frac:
+        raw = raw >> (have - frac)  # arithmetic shift: toward minus infinity
+      else:
+        raw = raw << (frac - have)
+    return _wrap(raw, t.raw_type)
+  raw, have = _raw(value, source)
+  if t.is_float:
+    return (raw.astype(np.float64) / float(1 << have)).astype(np_dtype(t))
+  # to an integer: toward zero
+  magnitude = np.abs(raw) >> have
+  return _as(np.where(raw < 0, -magnitude, magnitude), t)
+
+
+def _to(value, source: ir.Type, t: ir.Type):
+  if t.is_fixed or (source is not None and source.is_fixed):
+    return _convert(value, source, t)
+  return _as(value, t)
+
+
 def _trunc_div(a, b):
   """C++ integer division (toward zero); x/0 yields 0 instead of trapping."""
   if a.dtype.kind == 'u':
@@ -118,13 +160,19 @@ class _Evaluator:
       t = node.literal_type
       return np_dtype(t)(node.value), t
     if isinstance(node, ir.Cast):
-      value, _ = self(node.expr)
-      return _as(value, node.haoda_type), node.haoda_type
+      value, source = self(node.expr)
+      return _to(value, source, node.haoda_type), node.haoda_type
     if isinstance(node, ir.Unary):
       value, t = self(node.operand)
       for op in reversed(node.operator):
         if op == '!':
           value, t = np.asarray(value) == 0, ir.Type('bool')
+          continue
+        if t.is_fixed:
+          if op == '~':
+            raise TypeError('~ of a fixed-point value')
+          raw, frac = _raw(value, t)
+          value, t = (-raw if op == '-' else raw), ir.Type.exact_fixed(frac)
           continue
         t = ir._promote(t)
         value = _as(value, t)
@@ -151,6 +199,20 @@ class _Evaluator:
           if node.haoda_type == ir.FLOAT:  # float math mode
             return func(_as(args[0][0], ir.FLOAT)).astype(np.float32), ir.FLOAT
           return func(*[_as(v, ir.DOUBLE) for v, _ in args]), ir.DOUBLE
+      if any(at.is_fixed for _, at in args):
+        if node.name not in ir.SELECT_CALLS and node.name != 'abs':
+          raise TypeError('%s of a fixed-point value' % node.name)
+        raws = [_raw(v, at) for v, at in args]
+        frac = max(f for _, f in raws)
+        aligned = [r << (frac - f) for r, f in raws]
+        if node.name == 'abs':
+          value = np.abs(aligned[0])
+        else:
+          func = np.minimum if node.name == 'min' else np.maximum
+          value = aligned[0]
+          for other in aligned[1:]:
+            value = func(value, other)
+        return value, ir.Type.exact_fixed(frac)
       if node.name in ir.SELECT_CALLS:
         t = args[0][1]
         for _, at in args[1:]:
@@ -174,6 +236,21 @@ class _Evaluator:
       a, b = np.asarray(a) != 0, np.asarray(b) != 0
       return (np.logical_or(a, b) if op == '||' else np.logical_and(a, b),
               ir.Type('bool'))
+    if at.is_fixed or bt.is_fixed:
+      (ra, fa), (rb, fb) = _raw(a, at), _raw(b, bt)
+      if op == '*':
+        return ra * rb, ir.Type.exact_fixed(fa + fb)
+      frac = max(fa, fb)
+      ra, rb = ra << (frac - fa), rb << (frac - fb)
+      if op == '+':
+        return ra + rb, ir.Type.exact_fixed(frac)
+      if op == '-':
+        return ra - rb, ir.Type.exact_fixed(frac)
+      compare = {'==': np.equal, '!=': np.not_equal, '<=': np.less_equal,
+                 '>=': np.greater_equal, '<': np.less, '>': np.greater}
+      if op in compare:
+        return compare[op](ra, rb), ir.Type('bool')
+      raise TypeError('operator %s on fixed-point values' % op)
     t = ir.common_type(at, bt)
     a, b = _as(a, t), _as(b, t)
     if op in ('==', '!=', '<=', '>=', '<', '>'):
@@ -234,6 +311,8 @@ def run(stencil, inputs: Dict[str, np.ndarray],
       raise ValueError('all inputs must share one extent')
     if stmt.haoda_type.is_lowerable:
       arr = _wrap(arr, stmt.haoda_type)  # an ap_uint<N> array holds N bits
+    elif stmt.haoda_type.is_fixed and stmt.haoda_type.raw_type.is_lowerable:
+      arr = _wrap(arr, stmt.haoda_type.raw_type)
     data[name] = arr
 
   tensors = stencil.chronological_tensors
@@ -266,11 +345,11 @@ def run(stencil, inputs: Dict[str, np.ndarray],
       for let in tensor.lets:
         value, t = evaluator(let.expr)
         if let.haoda_type is not None:
-          value, t = _as(value, let.haoda_type), let.haoda_type
+          value, t = _to(value, t, let.haoda_type), let.haoda_type
         variables[let.name] = (value, t)
-      value, _ = evaluator(tensor.expr)
+      value, source = evaluator(tensor.expr)
       index = tuple(slice(box[d][0], box[d][1]) for d in reversed(range(dim)))
-      out[index] = _as(value, tensor.haoda_type)
+      out[index] = _to(value, source, tensor.haoda_type)
     data[tensor.name] = out
     if tensor.name in stencil.output_names or keep_intermediates:
       outputs[tensor.name] = out

@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Sequence
 
 from soda_b200 import ir, util
 from soda_b200.codegen.cuda import plan as planner
-from soda_b200.optimization import widths
+from soda_b200.optimization import fixed_point, widths
 
 DTYPE_CODES = {
     'uint8': 'SODA_CUDA_U8',
@@ -307,8 +307,9 @@ def emit_program(stencil,
                  options: Optional[Dict] = None) -> str:
   """Returns the text of the generated .cu file for ``stencil``."""
   options = dict(options or {})
-  # integer widths C++ does not have become containers + explicit wraps
-  stencil = widths.lower(stencil)
+  # fixed-point types become scaled integers, integer widths C++ does not
+  # have become containers + explicit wraps
+  stencil = widths.lower(fixed_point.lower(stencil))
   source_dim = stencil.dim
   if stencil.dim == 1:
     # a 1-D program runs as the 2-D program over an N x 1 grid

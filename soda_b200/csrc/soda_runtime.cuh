@@ -883,15 +883,6 @@ struct HostPipeline {
     return SODA_CUDA_OK;
   }
 
-  // SODA_CUDA_HOST_RAMP=0 keeps equal chunks (A/B measurements)
-  static bool host_ramp_enabled() {
-    static const bool enabled = [] {
-      const char* env = getenv("SODA_CUDA_HOST_RAMP");
-      return env == nullptr || env[0] != '0';
-    }();
-    return enabled;
-  }
-
   static int choose_chunks(const ProgramDesc& prog, const soda_cuda_plan* plan,
                            int slices) {
     int reach_lo = 0, reach_hi = 0;
@@ -978,14 +969,17 @@ struct HostPipeline {
       if (status != SODA_CUDA_OK) return status;
     }
 
-    // chunk bounds.  While the first chunk is uploaded nothing else can run,
-    // and nothing overlaps the download of the last one: when the chunk count
-    // is the pipeline's own choice, the chunks at both ends are shorter (a
-    // quarter, then half of an inner chunk), which cuts those two exposed
-    // copies to a quarter at the price of some redundant seam compute in four
-    // small chunks.  An explicit count (opts) keeps equal chunks.
+    // chunk bounds: equal chunks, or - a negative chunk count in opts - shorter
+    // chunks at both ends (a quarter, then half of an inner chunk), which
+    // shrinks the upload nothing can overlap (the first) and the download
+    // nothing overlaps (the last).  Measured on B200 for the 16384^2 x 64
+    // workload (profiles/r02_e2e_chunk_layouts.jsonl): 23.64 ms with 16 equal
+    // chunks against 23.95 ms ramped - the link is saturated in both
+    // directions either way (2.13 GB at the 98.8 GB/s both-way peak is 21.6
+    // ms) and the small chunks fill the GPU badly - so equal chunks are what
+    // the pipeline chooses by itself.
     std::vector<int> bound(chunks + 1), piece(chunks + 1);
-    const bool ramp = plan->host_chunks <= 0 && chunks >= 8 && host_ramp_enabled();
+    const bool ramp = plan->host_chunks < 0 && chunks >= 8;
     if (ramp) {
       // weights 1/4, 1/2, 1 ... 1, 1/2, 1/4 in quarter units
       std::vector<int> weight(chunks, 4);

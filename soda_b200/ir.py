@@ -36,11 +36,9 @@ class Type:
   Arbitrary widths (``uint6``, ``int27``, ``float18_3``) parse and print.  The
   widths C++ has (<cstdint> integers, float, double) and IEEE ``half`` execute
   as such; other integers of up to 63 bits are lowered to containers
-  (``is_lowerable``); ``c_type`` raises for what remains: fixed-point types
-  (the reference prints ``ap_fixed<N, M>``, whose arithmetic lives in the
-  Xilinx headers and which no reference test executes - nothing to pin a
-  restatement against) and custom floats (which the reference cannot print as
-  C either).
+  (``is_lowerable``), fixed-point types to scaled integers
+  (soda_b200/optimization/fixed_point.py); ``c_type`` raises for what remains:
+  custom floats, which the reference cannot print as C either.
   """
   __slots__ = ('_name',)
 
@@ -84,6 +82,31 @@ class Type:
     return bool(m and m.group(1) != 'float' and m.group(3) is not None)
 
   @property
+  def frac_bits(self) -> int:
+    """Fractional bits of a fixed-point type ``(u)intN_M`` (N bits in all, M of
+    them integer bits: the reference prints ``ap_(u)fixed<N, M>``); 0 for
+    every other type."""
+    m = _TYPE_RE.match(self._name)
+    if m and m.group(1) != 'float' and m.group(3) is not None:
+      return int(m.group(2)) - int(m.group(3))
+    return 0
+
+  @property
+  def raw_type(self) -> 'Type':
+    """The integer type of the same width that holds the scaled value of a
+    fixed-point type (``uint18_3`` -> ``uint18``)."""
+    if not self.is_fixed:
+      return self
+    m = _TYPE_RE.match(self._name)
+    return Type(m.group(1) + m.group(2))
+
+  @staticmethod
+  def exact_fixed(frac_bits: int) -> 'Type':
+    """Type of an exact fixed-point intermediate with ``frac_bits`` fractional
+    bits (``ap_fixed`` operators widen; here: 64 bits)."""
+    return Type('int64_%d' % (64 - frac_bits))
+
+  @property
   def width_in_bits(self) -> int:
     if self._name == 'float':
       return 32
@@ -125,6 +148,8 @@ class Type:
     arithmetic of ``ap_int`` as long as intermediates fit 63 bits (an
     ``ap_uint<40>`` occupies 8 bytes with the value zero-extended, so the bytes
     are those of the reference's array)."""
+    if self.is_fixed:
+      return self.raw_type.container
     if not self.is_lowerable:
       return self
     bits = self.width_in_bits

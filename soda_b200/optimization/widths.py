@@ -20,9 +20,9 @@ Exactness of the arithmetic in between is the same contract as for the
 standard narrow types: intermediates must fit in 32 bits
 (63 bits once a 33..63-bit value takes part: those are loaded as ``int64``),
 where C++ arithmetic and the widening ``ap_int`` arithmetic agree.
-Fixed-point (``uint18_3``) and custom float types stay unsupported: the former
-would be ``ap_fixed`` arithmetic from the Xilinx headers, which no reference
-test executes; the reference has no C type at all for the latter.
+Fixed-point types (``uint18_3``) are rewritten to such integers first
+(fixed_point.py); custom float types stay unsupported (the reference has no C
+type for them either).
 
 The oracle does not use this pass: oracle/golden.py and oracle/emit_cpp.py
 wrap natively, so that a mistake here cannot hide.
