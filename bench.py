@@ -296,7 +296,7 @@ def cpu_baseline_dataflow():
       'cores': 1,
       'kind': 'port (reference-style dataflow kernel, C simulation)',
       'sample': '%dx%d grid as one tile, %d of %d iterations, unroll factor 2, '
-                'kernel only (streams already tiled), g++ -O3 -march=native' %
+                'kernel only (streams already tiled), g++ -O3' %
                 (extent[0], extent[1], st.iterate, ITERATE),
       'modules': {k: counts[k] for k in ('load', 'forward', 'compute', 'store')},
       'fifos': counts['fifos'],
