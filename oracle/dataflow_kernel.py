@@ -48,7 +48,7 @@ import ctypes
 import hashlib
 import os
 import subprocess
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Tuple
 
 import numpy as np
 
