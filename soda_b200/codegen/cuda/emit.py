@@ -250,16 +250,6 @@ def _emit_pass(ns: str, stencil, pass_plan: planner.PassPlan,
     consts['kHaloLo1'] = pass_plan.halo_lo[1]
     consts['kValid1'] = pass_plan.valid[1]
   consts.update(tuning)
-  # 3-D: warps at each end of a tile whose patch rows reach into some node's
-  # dimension-1 halo; they run a copy of the step loop without those rows
-  consts['kEdgeWarps'] = 0
-  if dim == 3:
-    dead = max([0] + [max(n.halo_lo[1], n.halo_hi[1]) for n in nodes
-                      if n.kind == 'stage'])
-    edge = -(-dead // pass_plan.cy)
-    if edge and 2 * edge <= pass_plan.rows // pass_plan.cy and edge <= 2 and \
-        not options.get('no_edge_roles'):
-      consts['kEdgeWarps'] = edge
   for key, value in consts.items():
     lines.append('  static constexpr int {} = {};'.format(key, value))
   lines.append('  template <int N> using T = typename NodeType<N>::type;')
@@ -271,14 +261,8 @@ def _emit_pass(ns: str, stencil, pass_plan: planner.PassPlan,
           'statement %s loads more than 8 distinct tensors' % node.name)
     prods = ', '.join(map(str, node.prods + [0] * (8 - len(node.prods))))
     lines.append(
-        '      {{{kind}, {src}, {lag}, {ring}, {out}, {smem}, {reach}, {nprod}, {{{prods}}}, '
-        '{dead_lo}, {dead_hi}}},'
+        '      {{{kind}, {src}, {lag}, {ring}, {out}, {smem}, {reach}, {nprod}, {{{prods}}}}},'
         '  // {id}: {name}'.format(kind=0 if node.kind == 'input' else 1,
-                                  # 3-D: tile rows at both ends on which this
-                                  # node's value is never valid (its share of
-                                  # the dimension-1 halo): not evaluated
-                                  dead_lo=node.halo_lo[1] if dim == 3 else 0,
-                                  dead_hi=node.halo_hi[1] if dim == 3 else 0,
                                   src=node.src,
                                   lag=node.lag,
                                   ring=node.ring,

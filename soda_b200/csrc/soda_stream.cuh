@@ -51,11 +51,6 @@ struct NodeDesc {
   int smem_reach;  // 3-D: furthest dimension-1 offset at which it is read
   int nprod;
   int prod[kMaxProds];  // producer node per functor load slot
-  // 3-D: tile rows [0, dead_lo) and [kRows - dead_hi, kRows) of this node lie
-  // in its dimension-1 halo: whatever is computed there is never valid and
-  // never read by a valid cell
-  int dead_lo;
-  int dead_hi;
 };
 
 __host__ __device__ constexpr int floor_div(int a, int b) {
@@ -364,24 +359,7 @@ struct Access {
   }
 };
 
-// Whether patch row J of node N has to be evaluated.  Contexts that know at
-// compile time which tile rows their patch covers (Ctx::kRowBase >= 0: the
-// warps at the two ends of a 3-D tile run their own copy of the step loop)
-// skip the rows of the node's dimension-1 halo.  It has to be a compile-time
-// fact: a run-time test around the evaluation, even a warp-uniform one, cuts
-// the step into basic blocks that the rows can no longer be interleaved
-// across (measured: heat3d time block 2 0.222 -> 0.280 ms per pass).
-template <class Prog, class Ctx, int N, int J>
-__host__ __device__ constexpr bool row_is_live() {
-  if constexpr (Ctx::kRowBase < 0) {
-    return true;
-  } else {
-    return Ctx::kRowBase + J >= Prog::kNodes[N].dead_lo &&
-           Ctx::kRowBase + J < Prog::kRows - Prog::kNodes[N].dead_hi;
-  }
-}
-
-// every unit of every live patch row of node N
+// every unit of every patch row of node N
 template <class Prog, class Ctx, int N, int K = 0>
 __device__ __forceinline__ void eval_units(Ctx& ctx) {
   if constexpr (K < Prog::kCy * kUnitsOf<Prog>) {
@@ -389,10 +367,8 @@ __device__ __forceinline__ void eval_units(Ctx& ctx) {
     using F = typename Prog::template StageF<Prog::kNodes[N].src>;
     constexpr int J = K / kUnitsOf<Prog>;
     constexpr int I = K % kUnitsOf<Prog>;
-    if constexpr (row_is_live<Prog, Ctx, N, J>()) {
-      newest_units<N, J, Prog>(ctx)[I] =
-          cast_to<T>(F::eval(Access<Prog, Ctx, N, J, I>{ctx}));
-    }
+    newest_units<N, J, Prog>(ctx)[I] =
+        cast_to<T>(F::eval(Access<Prog, Ctx, N, J, I>{ctx}));
     eval_units<Prog, Ctx, N, K + 1>(ctx);
   }
 }
@@ -536,7 +512,6 @@ template <class Prog>
 struct Ctx2D {
   static constexpr bool kRotate = false;  // windows are shifted every step
   static constexpr int kPhase = 0;
-  static constexpr int kRowBase = -1;  // no dimension-1 tile in 2-D
   Rings<Prog> rings;
   const Params2D<Prog>& p;
   const unsigned char* slot_base;  // current slot of the TMA ring
@@ -808,13 +783,10 @@ struct Ctx3D {
 };
 
 // What the functors see during step (round start + U) of the unrolled loop.
-// kRowBase: tile row of the thread's patch row 0 when the warp's position in
-// the tile is a compile-time fact (edge warps), -1 otherwise.
-template <class Prog, int U, int kRowBase_ = -1>
+template <class Prog, int U>
 struct Step3D {
   static constexpr bool kRotate = true;
   static constexpr int kPhase = U;
-  static constexpr int kRowBase = kRowBase_;
   Rings<Prog>& rings;
   Ctx3D<Prog>& c;
 
@@ -1018,7 +990,7 @@ __device__ __forceinline__ void issue_plane_3d(const Params3D<Prog>& p,
 // the kernel rounds the number of steps up to a multiple of kUnroll (planes
 // past the end of the grid are zero-filled by TMA and nothing is stored for
 // them), so that the register windows rotate by renaming across the round.
-template <class Prog, int kRowBase, int U = 0>
+template <class Prog, int U = 0>
 __device__ __forceinline__ void round_3d(Rings<Prog>& rings, Ctx3D<Prog>& ctx,
                                          Mbarrier* full, int t_begin,
                                          int num_steps) {
@@ -1027,7 +999,7 @@ __device__ __forceinline__ void round_3d(Rings<Prog>& rings, Ctx3D<Prog>& ctx,
     constexpr int kStages = S::kStages;
     constexpr int kInDepth = Prog::kInDepth;  // input planes still readable
     const int step = ctx.step + U;
-    Step3D<Prog, U, kRowBase> st{rings, ctx};
+    Step3D<Prog, U> st{rings, ctx};
     const int slot = st.template slot<kStages, 0>();
     mbar_wait(&full[slot], (static_cast<unsigned>(step) / kStages) & 1u);
     step_nodes_3d<Prog>(st, t_begin + step);
@@ -1041,38 +1013,7 @@ __device__ __forceinline__ void round_3d(Rings<Prog>& rings, Ctx3D<Prog>& ctx,
                              ctx.x0, ctx.y0, t_begin + dead + kStages, &full[s]);
       }
     }
-    round_3d<Prog, kRowBase, U + 1>(rings, ctx, full, t_begin, num_steps);
-  }
-}
-
-// The step loop of a segment, for a warp whose patch starts at tile row
-// kRowBase (-1: anywhere, every row is evaluated).
-template <class Prog, int kRowBase>
-__device__ __forceinline__ void run_segment_3d(Rings<Prog>& rings,
-                                            Ctx3D<Prog>& ctx, Mbarrier* full,
-                                            int t_begin, int num_steps) {
-  for (ctx.step = 0; ctx.step < num_steps; ctx.step += Prog::kUnroll)
-    round_3d<Prog, kRowBase>(rings, ctx, full, t_begin, num_steps);
-}
-
-// Warp E from either end of the tile runs the loop specialised for its rows.
-template <class Prog, int E = 0>
-__device__ __forceinline__ void dispatch_segment_3d(Rings<Prog>& rings,
-                                                    Ctx3D<Prog>& ctx,
-                                                    Mbarrier* full, int t_begin,
-                                                    int num_steps) {
-  if constexpr (E < Prog::kEdgeWarps) {
-    const int warp = threadIdx.x >> 5;
-    if (warp == E) {
-      run_segment_3d<Prog, E * Prog::kCy>(rings, ctx, full, t_begin, num_steps);
-    } else if (warp == Prog::kWarps - 1 - E) {
-      run_segment_3d<Prog, Prog::kRows - (E + 1) * Prog::kCy>(
-          rings, ctx, full, t_begin, num_steps);
-    } else {
-      dispatch_segment_3d<Prog, E + 1>(rings, ctx, full, t_begin, num_steps);
-    }
-  } else {
-    run_segment_3d<Prog, -1>(rings, ctx, full, t_begin, num_steps);
+    round_3d<Prog, U + 1>(rings, ctx, full, t_begin, num_steps);
   }
 }
 
@@ -1124,7 +1065,8 @@ __global__ void __launch_bounds__(Prog::kWarps * 32, Prog::kMinBlocks)
   }
   cta_sync();
 
-  dispatch_segment_3d<Prog>(rings, ctx, full, t_begin, num_steps);
+  for (ctx.step = 0; ctx.step < num_steps; ctx.step += Prog::kUnroll)
+    round_3d<Prog>(rings, ctx, full, t_begin, num_steps);
 }
 
 }  // namespace soda
