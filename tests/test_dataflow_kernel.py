@@ -29,13 +29,13 @@ EXTRA = [
 ]
 
 
-def _oracle_path(st, extent, inputs, kernel, keep=None):
+def _oracle_path(st, extent, inputs, kernel):
   return run_data_path(
       st, extent, inputs,
       pack=lambda layout, dense: oracle_layout.tile(to_oracle(layout, st), dense),
       unpack=lambda layout, banks, dense: oracle_layout.untile(
           to_oracle(layout, st), banks, dense),
-      kernel=kernel, keep_banks=keep)
+      kernel=kernel)
 
 
 def _cases():

@@ -40,8 +40,7 @@ CASES = [
 ]
 
 
-def run_data_path(st, extent, inputs, pack, unpack, kernel=None,
-                  keep_banks=None):
+def run_data_path(st, extent, inputs, pack, unpack, kernel=None):
   layouts = {n: stream_layout.TensorLayout(st, n, extent)
              for n in st.input_names + st.output_names}
   first = layouts[st.input_names[0]]
@@ -63,8 +62,6 @@ def run_data_path(st, extent, inputs, pack, unpack, kernel=None,
     words = layouts[n].burst_width // layouts[n].elem_bits
     assert cycles * words <= layouts[n].elems_per_bank
   (kernel or stream_kernel.StreamKernel)(st).run(in_banks, out_banks, cycles)
-  if keep_banks is not None:
-    keep_banks.update(out_banks)
   outputs = {}
   for i, n in enumerate(st.output_names):
     dense = np.full(extent[::-1], 77,
