@@ -250,7 +250,11 @@ typedef struct soda_cuda_slab_opts {
   const void* nccl_id;     /* SODA_CUDA_NCCL_ID_BYTES bytes, identical on all ranks
                             * (native transport, world > 1) */
   int32_t reserved[8];     /* reserved[0] = 1: dry run - bounds, ghost depths and exchange
-                            * groups only (soda_cuda_slab_get_info); nothing is allocated */
+                            * groups only (soda_cuda_slab_get_info); nothing is allocated
+                            * reserved[1]: where soda_cuda_slab_run_host computes the chunks
+                            * that read ghost slices: 0 = by transport (NCCL: in their
+                            * natural place, the exchange over NVLink is quick; callback:
+                            * last), 1 = natural place, 2 = last */
 } soda_cuda_slab_opts;
 
 typedef struct soda_cuda_slab_info {

@@ -144,6 +144,7 @@ class SlabRunner:
                transport: str = 'auto',
                overlap: bool = True,
                host_chunks: int = 0,
+               edge_chunks: Optional[str] = None,
                segment: int = 0,
                dry_run: bool = False):
     self.program = program
@@ -174,6 +175,7 @@ class SlabRunner:
     opts.no_overlap = 0 if overlap else 1
     opts.host_chunks = host_chunks
     opts.reserved[0] = 1 if dry_run else 0
+    opts.reserved[1] = {None: 0, 'natural': 1, 'last': 2}[edge_chunks]
     self._callback = EXCHANGE_FN(self._exchange_callback)
     self._nccl_id = None
     if dry_run:

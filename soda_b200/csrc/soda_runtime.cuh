@@ -870,6 +870,10 @@ struct HostPipeline {
   int host_lo = 0, host_hi = 0;  // slices the host arrays hold
   int host_shift = 0;            // plan slice s is host slice s + host_shift
   bool ghosts_from_peers = false;
+  // whether chunks that read ghost slices are computed last (a transport of
+  // unknown speed) or in their natural place (NCCL over NVLink: the exchange
+  // of a few slices is over long before the first chunk's own upload is)
+  bool defer_edge_chunks = true;
   int (*after_edges)(void* user, cudaStream_t copy_in) = nullptr;
   int (*before_edge)(void* user, cudaStream_t compute) = nullptr;
   void* user = nullptr;
@@ -1016,17 +1020,30 @@ struct HostPipeline {
       SODA_CUDA_CHECK(cudaEventRecord(copied[k], plan->copy_in_stream));
     }
 
-    // compute order: chunks that read ghost slices from the neighbours last
+    // compute order.  A chunk that reads ghost slices has to wait for the
+    // exchange; with a transport of unknown speed such chunks go last.  With
+    // a fast one they stay in place: chunk 0 of a rank with a neighbour below
+    // would otherwise be uploaded first and computed last - one more upload
+    // before the first compute and two more downloads after the last one
+    // (N = 2, 16384^2 per rank: 32.5 ms per step).
     std::vector<int> order;
-    for (int k = 0; k < chunks; ++k) {
-      const bool edge = peers && (bound[k] - reach_lo < host_lo ||
-                                  bound[k + 1] + reach_hi > host_hi);
-      if (!edge) order.push_back(k);
+    size_t interior = 0;
+    if (peers && defer_edge_chunks) {
+      for (int k = 0; k < chunks; ++k) {
+        const bool edge = bound[k] - reach_lo < host_lo ||
+                          bound[k + 1] + reach_hi > host_hi;
+        if (!edge) order.push_back(k);
+      }
+      interior = order.size();
+      for (int k = 0; k < chunks; ++k)
+        if (std::find(order.begin(), order.end(), k) == order.end())
+          order.push_back(k);
+    } else {
+      for (int k = 0; k < chunks; ++k) order.push_back(k);
+      // the exchange is waited for before the first chunk (it reads the ghost
+      // slices below the slab or none at all)
+      interior = peers ? 0 : order.size();
     }
-    const size_t interior = order.size();
-    for (int k = 0; k < chunks; ++k)
-      if (std::find(order.begin(), order.end(), k) == order.end())
-        order.push_back(k);
 
     int lo[kMaxT][kMaxD], hi[kMaxT][kMaxD];
     default_boxes(prog, plan, true, lo, hi);

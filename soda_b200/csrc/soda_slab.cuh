@@ -185,6 +185,7 @@ struct soda_cuda_slab {
   std::vector<std::vector<int>> groups;
   soda_cuda_plan* plan = nullptr;  // local arrays, scratch, streams
   soda::rt::Transport* transport = nullptr;
+  bool defer_edge_chunks = true;  // host pipeline: see HostPipeline
 };
 
 namespace soda {
@@ -573,11 +574,14 @@ int soda_cuda_slab_create(const int32_t* global_extent, const soda_cuda_slab_opt
       } else {
         NcclTransport* nccl = new NcclTransport();
         slab->transport = nccl;
+        slab->defer_edge_chunks = false;  // NVLink: the exchange is quick
         status = nccl->init(opts->nccl_id, opts->rank, opts->world);
       }
 #endif
     }
   }
+  if (opts->reserved[1] == 1) slab->defer_edge_chunks = false;
+  if (opts->reserved[1] == 2) slab->defer_edge_chunks = true;
   if (status != SODA_CUDA_OK) {
     soda_cuda_slab_destroy(slab);
     return status;
@@ -685,6 +689,7 @@ int soda_cuda_slab_run_host(soda_cuda_slab* slab, const void* const* in_ptrs,
   pipe.own_hi = pipe.host_hi = slab->own_hi;
   pipe.host_shift = -slab->own_lo;
   pipe.ghosts_from_peers = slab->world > 1;
+  pipe.defer_edge_chunks = slab->defer_edge_chunks;
   pipe.after_edges = &SlabHooks::after_edges;
   pipe.before_edge = &SlabHooks::before_edge;
   pipe.user = &hooks;

@@ -23,7 +23,7 @@ def _free_port():
 
 def _worker(rank, world, port, name, overrides, time_block, extent, lib, seed,
             result_dir, exchange_every=None, expect_groups=None,
-            host_chunks=None):
+            host_chunks=None, edge_chunks=None):
   sys.path.insert(0, common.ROOT)
   os.environ['MASTER_ADDR'] = '127.0.0.1'
   os.environ['MASTER_PORT'] = str(port)
@@ -34,7 +34,8 @@ def _worker(rank, world, port, name, overrides, time_block, extent, lib, seed,
     prog = launcher.CudaProgram(lib)
     runner = multi_gpu.SlabRunner(prog, extent, torch.device('cpu'), rank=rank,
                                   world=world, exchange_every=exchange_every,
-                                  host_chunks=host_chunks or 0)
+                                  host_chunks=host_chunks or 0,
+                                  edge_chunks=edge_chunks)
     if expect_groups is not None:
       assert [len(g) for g in runner.groups] == expect_groups, runner.groups
     inputs = common.make_inputs(st, extent, seed=seed)
@@ -67,14 +68,15 @@ def _worker(rank, world, port, name, overrides, time_block, extent, lib, seed,
 
 def run_case(tmp_path, name, extent, world, time_block=None, options=None,
              seed=3, exchange_every=None, expect_groups=None, host_chunks=None,
-             **overrides):
+             edge_chunks=None, **overrides):
   from tests.emu import build_emu
   st = common.stencil(name, **overrides)
   lib = build_emu.build_emu_library(st, time_block=time_block, options=options)
   port = _free_port()
   mp.spawn(_worker,
            args=(world, port, name, overrides, time_block, extent, lib, seed,
-                 str(tmp_path), exchange_every, expect_groups, host_chunks),
+                 str(tmp_path), exchange_every, expect_groups, host_chunks,
+                 edge_chunks),
            nprocs=world, join=True)
   inputs = common.make_inputs(st, extent, seed=seed)
   want = common.oracle_outputs(st, inputs)
@@ -162,12 +164,17 @@ def test_default_groups_keep_the_ghost_small():
     ('heat3d', (40, 12, 40), 2, dict(time_block=2, iterate=4, host_chunks=3,
                                      options={'rows': 8})),
 ])
-def test_slab_host_pipeline(tmp_path, name, extent, world, kwargs):
+@pytest.mark.parametrize('edge_chunks', [None, 'natural'])
+def test_slab_host_pipeline(tmp_path, name, extent, world, kwargs, edge_chunks):
   """soda_cuda_slab_run_host: every rank's own slices in host arrays, chunked
   H2D / passes / D2H per rank, the input ghosts from the neighbours' uploads
   (one exchange per call); bit-identical to the single-rank oracle, bytes
   outside the valid box untouched."""
-  run_case(tmp_path, name, extent, world, exchange_every=-1, **kwargs)
+  # edge_chunks: where the chunks that read ghost slices are computed - last
+  # (the default of a callback transport) or in their natural place (what the
+  # NCCL transport does on GPUs)
+  run_case(tmp_path, name, extent, world, exchange_every=-1,
+           edge_chunks=edge_chunks, **kwargs)
 
 
 @pytest.mark.parametrize('name,extent,devices,kwargs', [
