@@ -18,6 +18,6 @@ for c in d['other_configs']:
   print(c.get('config'), c.get('value'), c.get('roofline',{}).get('frac'), c.get('parity',{}).get('bit_exact'), c.get('error'))
 PY
 tail -3 $O/r02m_bench.err
-timeout 600 ncu -k regex:soda --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/r02m_bench_launches.csv python bench.py --steps 2 --warmup 1 --headline-only > $O/r02m_ncu_list.log 2>&1; echo "ncu list exit $?"
+timeout 600 ncu -k regex:soda --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02m_bench_launches.csv python bench.py --steps 2 --warmup 1 --headline-only > $O/r02m_ncu_list.log 2>&1; echo "ncu list exit $?"
 SODA_CUDA_AUTOTUNE=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:soda_stream2d --launch-skip 13 --launch-count 1 -o $O/r02m_prof_j2d_tb6 python bench.py --steps 2 --warmup 1 --headline-only > $O/r02m_ncu_full.log 2>&1; echo "ncu full exit $?"
 SODA_CUDA_AUTOTUNE=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:soda_stream3d -s 1 -c 1 -o $O/r02m_prof_denoise3d python tools/run_one.py denoise3d 512,512,512 --reps 1 --warmup 1 > $O/r02m_ncu_denoise3d.log 2>&1; echo "ncu denoise3d exit $?"
