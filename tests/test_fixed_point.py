@@ -173,3 +173,72 @@ output float18_3: b(0, 0) = a(0, 0) + a(1, 0)
 ''')
   with pytest.raises(util.SemanticError):
     emit.emit_program(st)
+
+
+def _random_fixed_program(seed):
+  """A seeded random fixed-point program: two stages over one input, types
+  with random widths / integer bits, sums, differences and products of taps,
+  integer literals, casts to other fixed-point types, comparisons."""
+  rng = np.random.default_rng(7000 + seed)
+
+  def fixed_type(max_bits=18):
+    bits = int(rng.integers(6, max_bits + 1))
+    integer = int(rng.integers(1, bits))
+    return '%sint%d_%d' % ('u' if rng.random() < 0.5 else '', bits, integer)
+
+  def tap(name, store=(0, 0)):
+    return '%s(%d, %d)' % (name, store[0] + int(rng.integers(-1, 2)),
+                           store[1] + int(rng.integers(-1, 2)))
+
+  def expr(name):
+    terms = ['%s(0, 0)' % name]
+    for _ in range(int(rng.integers(1, 4))):
+      kind = rng.integers(5)
+      t = tap(name)
+      if kind == 0:
+        terms.append(t)
+      elif kind == 1:
+        terms.append('%s * %d' % (t, int(rng.integers(2, 6))))
+      elif kind == 2:
+        terms.append('%s * %s' % (t, tap(name)))
+      elif kind == 3:
+        terms.append('%s(%s)' % (fixed_type(12), t))
+      else:
+        terms.append('max(%s, %s)' % (t, tap(name)))
+    text = terms[0]
+    for term in terms[1:]:
+      text += (' + ' if rng.random() < 0.6 else ' - ') + term
+    if rng.random() < 0.3:
+      text = '(%s) * (%s > %s)' % (text, tap(name), tap(name))
+    return text
+
+  in_t, mid_t, out_t = fixed_type(16), fixed_type(), fixed_type()
+  return '''kernel: fxrnd%d
+burst width: 64
+unroll factor: 2
+iterate: %d
+input %s: a(32, *)
+local %s: m(0, 0) = %s
+output %s: b(0, 0) = %s
+''' % (seed, 1 if in_t != out_t else int(rng.integers(1, 3)), in_t, mid_t,
+       expr('a'), out_t, expr('m'))
+
+
+@pytest.mark.parametrize('seed', range(24))
+def test_random_fixed_point_programs(seed):
+  """The native NumPy evaluation, NumPy on the rewritten program and g++ on the
+  rewritten program agree bit for bit on seeded random fixed-point programs."""
+  st = sodac.compile_source(_random_fixed_program(seed))
+  extent = (40, 11)
+  rng = np.random.default_rng(seed)
+  dtype = golden.np_dtype(st.input_stmts[0].haoda_type)
+  inputs = {'a': rng.integers(0, 2**31, extent[::-1]).astype(dtype)}
+  native = golden.run(st, inputs)
+  low = widths.lower(fixed_point.lower(st))
+  assert not fixed_point.has_fixed_types(low)
+  rewritten = golden.run(low, inputs)
+  compiled = emit_cpp.Oracle(st).run(inputs)
+  index = common.box_index(st.valid_box('b', extent))
+  assert native['b'][index].size > 0
+  assert np.array_equal(native['b'][index], rewritten['b'][index])
+  assert np.array_equal(native['b'][index], compiled['b'][index])
