@@ -54,6 +54,12 @@ CONFIGS = {
                             extent=(16384, 16384), time_block=8),
     'C3_heat3d': dict(program='heat3d', overrides={'iterate': 32},
                       extent=(512, 512, 512)),
+    # heat3d's coefficients are powers of two: with --cuda-pow2-fma every
+    # `c * x + acc` is one FFMA (1 FMUL + 6 FFMA instead of 7 FMUL + 6 FADD per
+    # update), exact unless c * x is subnormal (soda::fma_pow2)
+    'C3_heat3d_pow2_fma': dict(program='heat3d', overrides={'iterate': 32},
+                               extent=(512, 512, 512),
+                               options={'pow2_fma': True}),
     'C3_jacobi3d': dict(program='jacobi3d', overrides={'iterate': 32},
                         extent=(512, 512, 512)),
     'C4_denoise3d': dict(program='denoise3d', overrides={},
@@ -72,7 +78,8 @@ CONFIGS = {
 # communicator (default), 'torch' = torch.distributed point-to-point callbacks
 TRANSPORT = os.environ.get('SODA_BENCH_TRANSPORT', 'nccl')
 HEADLINE = 'C2_jacobi2d'
-OTHER = ('C1_blur', 'C2_jacobi2d_tb8', 'C3_heat3d', 'C3_jacobi3d', 'C4_denoise3d',
+OTHER = ('C1_blur', 'C2_jacobi2d_tb8', 'C3_heat3d', 'C3_heat3d_pow2_fma',
+         'C3_jacobi3d', 'C4_denoise3d',
          'C4_denoise3d_cr', 'C4_denoise3d_float_math')
 WIDTH, HEIGHT = CONFIGS[HEADLINE]['extent']
 ITERATE = CONFIGS[HEADLINE]['overrides']['iterate']
@@ -91,7 +98,8 @@ def config_program(key):
   from soda_b200.codegen import cuda as cuda_backend
   st = config_stencil(key)
   return st, cuda_backend.compile_stencil(
-      st, time_block=CONFIGS[key].get('time_block'))
+      st, time_block=CONFIGS[key].get('time_block'),
+      options=CONFIGS[key].get('options'))
 
 
 def measured_hbm_peak():
@@ -491,7 +499,9 @@ def run_device_config(key, device, stream, steps, warmup, peak, windows=8):
       'workload': '%s %s iterate %d%s' %
                   (CONFIGS[key]['program'] + (
                       ' --cuda-time-block %d' % CONFIGS[key]['time_block']
-                      if CONFIGS[key].get('time_block') else ''),
+                      if CONFIGS[key].get('time_block') else '') + ''.join(
+                          ' --cuda-%s' % k.replace('_', '-')
+                          for k in (CONFIGS[key].get('options') or {})),
                    'x'.join(map(str, extent)),
                    st.iterate, ''.join(
                        ' --%s %s' % (k.replace('_', '-'), v)

@@ -75,6 +75,13 @@ def add_arguments(parser) -> None:
                       'bit-identical to g++ without -ffp-contract)')
 
 
+  parser.add_argument('--cuda-pow2-fma', action='store_true',
+                      dest='cuda_pow2_fma',
+                      help='fuse `c * x + y` when the float literal c is a '
+                      'power of two: the product is exact, so the result is '
+                      'the un-fused one unless c * x is subnormal')
+
+
 def options_from_args(args: Optional[argparse.Namespace]) -> Dict:
   get = lambda name: getattr(args, name, None) if args is not None else None
   options = {
@@ -89,6 +96,7 @@ def options_from_args(args: Optional[argparse.Namespace]) -> Dict:
       'no_pipeline': bool(get('cuda_no_pipeline')),
       'fast_fp': bool(get('cuda_fast_fp')),
       'no_pack': bool(get('cuda_no_pack')),
+      'pow2_fma': bool(get('cuda_pow2_fma')),
   }
   return {k: v for k, v in options.items() if v}
 

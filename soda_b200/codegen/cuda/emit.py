@@ -55,7 +55,40 @@ class _FunctorPrinter(ir.CPrinter):
   occur only in never-stored halo cells) - C++ semantics are unchanged for
   non-zero divisors."""
 
+  pow2_fma = False  # --cuda-pow2-fma: see soda::fma_pow2 (soda_stream.cuh)
+
+  @staticmethod
+  def _pow2_product(node):
+    """(coefficient literal, other factor) of ``c * x`` / ``x * c`` with ``c`` a
+    float literal that is a power of two and ``x`` a float value, else None."""
+    node = ir.unwrap(node)
+    if not isinstance(node, ir.MulDiv) or tuple(node.operator) != ('*',) or \
+        len(node.operand) != 2 or ir.result_type(node) != ir.FLOAT:
+      return None
+    for lit, other in (node.operand, node.operand[::-1]):
+      lit = ir.unwrap(lit)
+      if isinstance(lit, ir.Num) and lit.literal_type == ir.FLOAT and \
+          ir.result_type(other) == ir.FLOAT:
+        value = float(lit.value)
+        if value > 0 and math.frexp(value)[0] == 0.5:
+          return lit, other
+    return None
+
   def __call__(self, node):
+    if self.pow2_fma and isinstance(node, ir.AddSub) and not node.singleton \
+        and ir.result_type(node) == ir.FLOAT:
+      # left to right, as C++ evaluates the chain; a term `c * x` with a
+      # power-of-two literal c joins the running sum in one fused operation
+      text = self(node.operand[0])
+      for operator, operand in zip(node.operator, node.operand[1:]):
+        product = self._pow2_product(operand)
+        if product is not None and ir.result_type(operand) == ir.FLOAT:
+          lit, other = product
+          text = 'soda::fma_pow2({}{}, {}, {})'.format(
+              '-' if operator == '-' else '', lit.c_literal, self(other), text)
+        else:
+          text = '({} {} {})'.format(text, operator, self(operand))
+      return text
     if isinstance(node, ir.Cast):
       # spelled so that the same functor text works for scalar cells and for
       # packed fp32 pairs (soda::cast_to<float>(F2) is the identity)
@@ -80,7 +113,8 @@ class _FunctorPrinter(ir.CPrinter):
 
 
 def _functor(desc: planner.StageDesc, dim: int,
-             param_sizes: Optional[Dict[str, List[int]]] = None) -> List[str]:
+             param_sizes: Optional[Dict[str, List[int]]] = None,
+             pow2_fma: bool = False) -> List[str]:
   stmt = desc.stmt
   slots = {name: k for k, name in enumerate(desc.slots)}
   st_idx = stmt.ref.idx
@@ -107,6 +141,7 @@ def _functor(desc: planner.StageDesc, dim: int,
   printer = _FunctorPrinter(ref_printer,
                             min_name='soda_gen::soda_min',
                             max_name='soda_gen::soda_max')
+  printer.pow2_fma = pow2_fma
   ctype = stmt.haoda_type.c_type
   lines = [
       '// {}'.format(str(stmt).replace('\n', '\n// ')),
@@ -365,7 +400,8 @@ def emit_program(stencil,
       'template <int F> struct Stage;',
   ]
   for desc in stages:
-    lines.extend(_functor(desc, dim, param_sizes))
+    lines.extend(_functor(desc, dim, param_sizes,
+                          pow2_fma=bool(options.get('pow2_fma'))))
   lines.append('}  // namespace soda_gen')
   lines.append('')
   lines.append('namespace soda_gen {')

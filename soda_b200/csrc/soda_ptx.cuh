@@ -219,6 +219,17 @@ __device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
       : "l"(a.bits), "l"(b.bits), "l"(soda_neg_zero_pair));
   return r;
 }
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+  F2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(r.bits)
+      : "l"(a.bits), "l"(b.bits), "l"(c.bits));
+  return r;
+}
+// fused multiply-add that --fmad=false does not touch (an explicit request)
+__device__ __forceinline__ float fma_rn(float a, float b, float c) {
+  return __fmaf_rn(a, b, c);
+}
 // A pair assembled from two registers that were loaded as part of a wider
 // vector (LDS.128) is only a register copy to ptxas, which then re-assembles it
 // with two MOVs at every use.  Adding a zero that is only known at run time

@@ -96,6 +96,26 @@ __device__ __forceinline__ F2 operator*(F2 a, S b) { return f2_mul(a, f2_splat(f
 template <typename S>
 __device__ __forceinline__ F2 operator*(S a, F2 b) { return f2_mul(f2_splat(float(a)), b); }
 
+// c * x + acc in one rounding, for a coefficient c that is a power of two
+// (--cuda-pow2-fma).  The product c * x is then exact, so rounding c * x + acc
+// once is what rounding the product and then the sum gives - except when
+// c * x falls into the subnormal range (|x| < 2^-126 / c), where the separate
+// product would lose bits: the result can then differ in the last place when
+// acc is as tiny.  Opt-in for that reason; the functor emitter only uses it
+// for float literals that are powers of two.
+__device__ __forceinline__ float fma_pow2(float c, float x, float acc) {
+  return fma_rn(c, x, acc);
+}
+__device__ __forceinline__ F2 fma_pow2(float c, F2 x, F2 acc) {
+  return f2_fma(f2_splat(c), x, acc);
+}
+__device__ __forceinline__ F2 fma_pow2(float c, F2 x, float acc) {
+  return f2_fma(f2_splat(c), x, f2_splat(acc));
+}
+__device__ __forceinline__ F2 fma_pow2(float c, float x, F2 acc) {
+  return f2_fma(f2_splat(c), f2_splat(x), acc);
+}
+
 template <typename To, typename From>
 __device__ __forceinline__ auto cast_to(From v) {
   if constexpr (std::is_same<From, F2>::value) {

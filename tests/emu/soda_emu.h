@@ -333,6 +333,10 @@ inline F2 f2_add(F2 a, F2 b) { return F2{a.lo + b.lo, a.hi + b.hi}; }
 inline F2 f2_sub(F2 a, F2 b) { return F2{a.lo - b.lo, a.hi - b.hi}; }
 inline F2 f2_mul(F2 a, F2 b) { return F2{a.lo * b.lo, a.hi * b.hi}; }
 inline F2 f2_neg(F2 a) { return F2{-a.lo, -a.hi}; }
+inline float fma_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline F2 f2_fma(F2 a, F2 b, F2 c) {
+  return F2{std::fmaf(a.lo, b.lo, c.lo), std::fmaf(a.hi, b.hi, c.hi)};
+}
 
 inline bool warp_any(bool flag) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

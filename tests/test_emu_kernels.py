@@ -112,6 +112,47 @@ def test_ramped_host_chunks_under_emulation(name, kwargs):
   run_case(name, host_chunks=-8, **kwargs)
 
 
+POW2_2D = '''kernel: pow2_2d
+burst width: 64
+unroll factor: 2
+iterate: 3
+input float: a(32, *)
+output float: b(0, 0) = .5f * a(0, 0) + a(1, 0) * .125f + .3f * a(-1, 0) - .125f * a(0, 1) + (a(0, -1) * .125f)
+'''
+
+
+@pytest.mark.parametrize('name,kwargs', [
+    ('heat3d', dict(extent=(40, 12, 20), time_block=2, iterate=4,
+                    options={'rows': 8, 'pow2_fma': True})),
+    (POW2_2D, dict(extent=(300, 40), time_block=3,
+                   options={'pow2_fma': True})),
+    (POW2_2D, dict(extent=(300, 40), time_block=1,
+                   options={'pow2_fma': True, 'no_pack': True})),
+])
+def test_fused_power_of_two_coefficients_under_emulation(name, kwargs):
+  """--cuda-pow2-fma (soda::fma_pow2): fused `c * x + acc` for power-of-two
+  literals only (`.3f * a` stays a product and a sum); equal to the un-fused
+  oracle bit for bit on data in the normal range, scalar and packed."""
+  from soda_b200 import sodac
+  from soda_b200.codegen.cuda import emit
+  if name == POW2_2D:
+    st = sodac.compile_source(name)
+    source = emit.emit_program(st, kwargs['time_block'], kwargs['options'])
+    assert source.count('soda::fma_pow2(') == 3  # the first term stays a product
+    assert '(.3f * ' in source
+    prog = launcher.CudaProgram(build_emu.build_emu_library(
+        st, time_block=kwargs['time_block'], options=kwargs['options']))
+    extent = kwargs['extent']
+    inputs = common.make_inputs(st, extent, seed=5)
+    outputs = {n: np.full(extent[::-1], 77, dtype=d)
+               for n, d in zip(prog.output_names, prog.output_dtypes)}
+    prog.run_host(inputs, outputs)
+    common.assert_matches_oracle(st, extent, outputs,
+                                 common.oracle_outputs(st, inputs), sentinel=77)
+  else:
+    run_case(name, **kwargs)
+
+
 ONE_SIDED_2D_NEG = '''kernel: one_sided_neg
 burst width: 64
 unroll factor: 2

@@ -88,6 +88,14 @@ def test_c3_512_cubed(key, time_block):
   check(st, prog, bench.CONFIGS[key]['extent'], windows=12)
 
 
+def test_c3_heat3d_with_fused_power_of_two_coefficients():
+  """--cuda-pow2-fma: `c * x + acc` with a power-of-two literal c in one FFMA;
+  the product is exact, so on data in the normal range the result is the
+  un-fused one, bit for bit."""
+  st, prog = bench.config_program('C3_heat3d_pow2_fma')
+  check(st, prog, bench.CONFIGS['C3_heat3d_pow2_fma']['extent'], windows=12)
+
+
 @pytest.mark.parametrize('key', ['C4_denoise3d', 'C4_denoise3d_cr'])
 def test_c4_denoise3d_512_cubed(key):
   st, prog = bench.config_program(key)
