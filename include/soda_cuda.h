@@ -75,7 +75,7 @@ typedef struct soda_cuda_opts {
   int32_t device;        /* CUDA device ordinal; -1 = current device */
   void* stream;          /* cudaStream_t; NULL = the default stream */
   int32_t segment;       /* output slices per CTA along the streamed dimension; 0 = auto:
-                          * the first launch of a pass on a large grid (>= 2^24 cells)
+                          * the first launch of a pass on a large window (>= 2^22 cells)
                           * times a few candidate lengths with CUDA events on `stream`
                           * and synchronises on them once (the pass is idempotent); later
                           * launches of the same shape reuse the winner.  Set a length, or

@@ -475,6 +475,16 @@ inline bool autotune_enabled() {
   return enabled;
 }
 
+// Launches over fewer cells than this use the rule of choose_segment().
+// SODA_CUDA_TUNE_MIN_CELLS_LOG2 overrides the exponent (experiments).
+inline long long tune_min_cells() {
+  static const long long value = [] {
+    const char* env = getenv("SODA_CUDA_TUNE_MIN_CELLS_LOG2");
+    return 1LL << (env != nullptr ? atoi(env) : 22);
+  }();
+  return value;
+}
+
 inline int launch_tuned(const ProgramDesc& prog, int variant, PassArgs a) {
   const PassImpl& impl = prog.impls[variant];
   const int dim = prog.info.dim, s_dim = dim - 1;
@@ -488,7 +498,13 @@ inline int launch_tuned(const ProgramDesc& prog, int variant, PassArgs a) {
   }
   const int slices = hi - lo;
   const int min_segment = impl.warmup * 2 > 8 ? impl.warmup * 2 : 8;
-  if (a.segment != 0 || !autotune_enabled() || cells < (1LL << 24) ||
+  // 4 Mi cells and up: the chunk windows of the host pipeline (1/16 to 1/64 of
+  // a grid) are measured too.  By the rule of choose_segment() a 16384 x 640
+  // window of the bench kernel is 4 segments = 136 CTAs, under one wave: the 11
+  // passes of such a chunk took 0.94 ms against 0.42 ms with the measured
+  // choice, more than the chunk's upload (0.74 ms), so that 24 chunks and
+  // more ran compute-bound (profiles/r02_pipeline_chunk_compute_old_new_threshold.jsonl)
+  if (a.segment != 0 || !autotune_enabled() || cells < tune_min_cells() ||
       slices < 4 * min_segment)
     return impl.launch(a);
 
@@ -500,7 +516,9 @@ inline int launch_tuned(const ProgramDesc& prog, int variant, PassArgs a) {
   cudaGetDevice(&key.device);
   for (int d = 0; d < dim; ++d) key.extent[d] = a.extent[d];
   // store boxes that differ by a few slices (the shrinking windows of an
-  // exchange group, multi_gpu.py) share one measurement
+  // exchange group, multi_gpu.py; the chunk windows of the host pipeline,
+  // whose heights differ by one) share one measurement
+  key.extent[s_dim] = a.extent[s_dim] / 64;
   key.lo = 0;
   key.hi = slices / 64;
   std::lock_guard<std::mutex> lock(mutex);
@@ -880,9 +898,66 @@ struct HostPipeline {
   // state between issue() and finish()
   std::vector<cudaEvent_t> events;
   int result = SODA_CUDA_OK;
+  // SODA_CUDA_PIPELINE_TRACE=1: when every chunk's upload, compute and download
+  // ended (ms after the call's first queued operation) on stderr, one JSON line
+  // per call.  The pipeline's own events carry the times (created with timing
+  // in this mode) plus one more record per download: a diagnostic, not for
+  // timed runs.
+  struct Trace {
+    cudaEvent_t start = nullptr;
+    std::vector<cudaEvent_t> marks[3];  // upload (piece order), compute, download (compute order)
+    std::vector<int> order, rows;
+  } trace;
+  static bool trace_enabled() {
+    static const bool enabled = [] {
+      const char* env = getenv("SODA_CUDA_PIPELINE_TRACE");
+      return env != nullptr && env[0] != '0';
+    }();
+    return enabled;
+  }
+  int mark(int which, cudaStream_t stream) {
+    if (!trace_enabled()) return SODA_CUDA_OK;
+    cudaEvent_t event;
+    SODA_CUDA_CHECK(cudaEventCreate(&event));
+    events.push_back(event);
+    if (which < 0) {
+      trace.start = event;
+    } else {
+      trace.marks[which].push_back(event);
+    }
+    SODA_CUDA_CHECK(cudaEventRecord(event, stream));
+    return SODA_CUDA_OK;
+  }
+  void print_trace() {
+    if (trace.start == nullptr) return;
+    static const char* const names[3] = {"upload_end", "compute_end", "download_end"};
+    std::string line = "{\"pipeline_trace\": {\"chunks\": " +
+                       std::to_string(trace.order.size());
+    auto list = [&](const char* name, const std::vector<int>& values) {
+      line += std::string(", \"") + name + "\": [";
+      for (size_t i = 0; i < values.size(); ++i)
+        line += (i ? ", " : "") + std::to_string(values[i]);
+      line += "]";
+    };
+    list("compute_order", trace.order);
+    list("chunk_slices", trace.rows);
+    for (int w = 0; w < 3; ++w) {
+      line += std::string(", \"") + names[w] + "_ms\": [";
+      for (size_t i = 0; i < trace.marks[w].size(); ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, trace.start, trace.marks[w][i]);
+        char text[32];
+        snprintf(text, sizeof(text), "%s%.3f", i ? ", " : "", ms);
+        line += text;
+      }
+      line += "]";
+    }
+    fprintf(stderr, "%s}}\n", line.c_str());
+  }
 
   int new_event(cudaEvent_t* event) {
-    SODA_CUDA_CHECK(cudaEventCreateWithFlags(event, cudaEventDisableTiming));
+    SODA_CUDA_CHECK(cudaEventCreateWithFlags(
+        event, trace_enabled() ? cudaEventDefault : cudaEventDisableTiming));
     events.push_back(*event);
     return SODA_CUDA_OK;
   }
@@ -904,8 +979,11 @@ struct HostPipeline {
       chunks = 1;
       if (bytes >= (32LL << 20)) {
         // chunks of at least 8x the reach: at most 12.5 % redundant compute at
-        // the seams, and windows tall enough to fill the GPU (32 chunks of the
-        // 16384^2 x 64 workload were measured slower than 16: 30.9 vs 25.8 ms)
+        // the seams.  More chunks shorten the last download but not the call:
+        // 16 / 24 / 32 / 48 / 64 chunks of the 16384^2 x 64 workload take 23.6 /
+        // 23.5 / 23.7 / 24.3 / 24.8 ms, the uploads run back to back at 43-47
+        // GB/s and lose about 0.07 ms per chunk to the passes' HBM traffic
+        // (profiles/r02_e2e_chunks_tuner_threshold.jsonl, r02_pipeline_trace_summary.txt)
         chunks = slices / (8 * (reach > 0 ? reach : 1));
         if (chunks > 16) chunks = 16;
         if (chunks < 1) chunks = 1;
@@ -960,6 +1038,8 @@ struct HostPipeline {
     if (status != SODA_CUDA_OK) return status;
     SODA_CUDA_CHECK(cudaEventRecord(start_event, plan->stream));
     SODA_CUDA_CHECK(cudaStreamWaitEvent(plan->copy_in_stream, start_event, 0));
+    status = mark(-1, plan->copy_in_stream);
+    if (status != SODA_CUDA_OK) return status;
 
     const bool peers = ghosts_from_peers && after_edges != nullptr;
     if (peers) {
@@ -977,11 +1057,13 @@ struct HostPipeline {
     // chunks at both ends (a quarter, then half of an inner chunk), which
     // shrinks the upload nothing can overlap (the first) and the download
     // nothing overlaps (the last).  Measured on B200 for the 16384^2 x 64
-    // workload (profiles/r02_e2e_chunk_layouts.jsonl): 23.64 ms with 16 equal
-    // chunks against 23.95 ms ramped - the link is saturated in both
-    // directions either way (2.13 GB at the 98.8 GB/s both-way peak is 21.6
-    // ms) and the small chunks fill the GPU badly - so equal chunks are what
-    // the pipeline chooses by itself.
+    // workload: 24.40 ms with 16 equal chunks against 24.33 ms ramped on the
+    // same box (profiles/r02_e2e_chunks_tuner_threshold.jsonl) - the copy-out
+    // stream is busy without a gap from the first chunk's compute to the end
+    // of the call, so what remains after the last upload is one inner chunk's
+    // download whatever the sizes of the chunks after it
+    // (profiles/r02_pipeline_trace_summary.txt) - so equal chunks are what the
+    // pipeline chooses by itself.
     std::vector<int> bound(chunks + 1), piece(chunks + 1);
     const bool ramp = plan->host_chunks < 0 && chunks >= 8;
     if (ramp) {
@@ -1018,6 +1100,7 @@ struct HostPipeline {
       status = upload(piece[k], piece[k + 1]);
       if (status != SODA_CUDA_OK) return status;
       SODA_CUDA_CHECK(cudaEventRecord(copied[k], plan->copy_in_stream));
+      if (trace_enabled()) trace.marks[0].push_back(copied[k]);
     }
 
     // compute order.  A chunk that reads ghost slices has to wait for the
@@ -1062,10 +1145,13 @@ struct HostPipeline {
              piece[last_needed + 1] < bound[k + 1] + reach_hi)
         ++last_needed;
       SODA_CUDA_CHECK(cudaStreamWaitEvent(plan->stream, copied[last_needed], 0));
+      trace.order.push_back(k);
+      trace.rows.push_back(bound[k + 1] - bound[k]);
       status = run_passes_window(plan, plan->d_in, pitches, plan->d_out, pitches,
                                  bound[k], bound[k + 1]);
       if (status != SODA_CUDA_OK) return status;
       SODA_CUDA_CHECK(cudaEventRecord(computed[k], plan->stream));
+      if (trace_enabled()) trace.marks[1].push_back(computed[k]);
       SODA_CUDA_CHECK(cudaStreamWaitEvent(plan->copy_out_stream, computed[k], 0));
       for (int o = 0; o < n_out; ++o) {
         int o_lo[kMaxD], o_hi[kMaxD];
@@ -1083,6 +1169,8 @@ struct HostPipeline {
                           prog.out_elem_bytes[o], o_lo, o_hi, false, host_shift);
         if (status != SODA_CUDA_OK) return status;
       }
+      status = mark(2, plan->copy_out_stream);
+      if (status != SODA_CUDA_OK) return status;
     }
     return SODA_CUDA_OK;
   }
@@ -1093,6 +1181,9 @@ struct HostPipeline {
     if (plan->copy_in_stream) sync_in = cudaStreamSynchronize(plan->copy_in_stream);
     cudaError_t sync_compute = cudaStreamSynchronize(plan->stream);
     if (plan->copy_out_stream) sync_out = cudaStreamSynchronize(plan->copy_out_stream);
+    if (issue_status == SODA_CUDA_OK && sync_in == cudaSuccess &&
+        sync_compute == cudaSuccess && sync_out == cudaSuccess)
+      print_trace();
     for (cudaEvent_t event : events) cudaEventDestroy(event);
     events.clear();
     if (issue_status != SODA_CUDA_OK) return issue_status;
