@@ -230,6 +230,16 @@ inline LaunchShape& last_launch_shape() {
   return shape;
 }
 
+// SODA_CUDA_WAVE_RULE=0 (experiments): choose_segment() without its
+// fill-one-wave-first clause.
+inline bool wave_rule_enabled() {
+  static const bool enabled = [] {
+    const char* env = getenv("SODA_CUDA_WAVE_RULE");
+    return env == nullptr || env[0] != '0';
+  }();
+  return enabled;
+}
+
 // Segments along the streamed dimension, by rule: enough CTAs for about four
 // waves, but long enough that the warm-up slices stay a small fraction.  Large
 // grids replace the rule by a measurement (launch_tuned below).
@@ -243,6 +253,19 @@ inline int choose_segment(int slices, int ctas_per_slice_set, int warmup,
   long long max_segments = slices / min_segment;
   if (max_segments < 1) max_segments = 1;
   if (segments > max_segments) segments = max_segments;
+  // A window too short for that many long segments would leave SMs without a
+  // CTA (a 16384 x 640 window of the bench kernel: 4 segments x 34 CTAs on 148
+  // SMs, 0.94 ms for 11 passes against 0.42 ms with 17 segments): fill one
+  // wave first, with segments down to 4x the warm-up.
+  const long long one_wave = static_cast<long long>(kNumSms) * ctas_per_sm;
+  const long long per_set = ctas_per_slice_set > 0 ? ctas_per_slice_set : 1;
+  if (segments * per_set < one_wave && wave_rule_enabled()) {
+    const int short_segment = warmup * 4 > 16 ? warmup * 4 : 16;
+    long long relaxed = slices / short_segment;
+    const long long wanted = (one_wave + per_set - 1) / per_set;
+    if (relaxed > wanted) relaxed = wanted;
+    if (relaxed > segments) segments = relaxed;
+  }
   return ceil_div(slices, static_cast<int>(segments));
 }
 
