@@ -985,8 +985,28 @@ struct HostPipeline {
     return SODA_CUDA_OK;
   }
 
+  // SODA_CUDA_CHUNK_WEIGHTS=w0,w1,... (experiments): that many chunks, of
+  // lengths in these proportions, whatever the options ask for.
+  static const std::vector<double>& env_weights() {
+    static const std::vector<double> weights = [] {
+      std::vector<double> w;
+      const char* env = getenv("SODA_CUDA_CHUNK_WEIGHTS");
+      while (env != nullptr && *env != 0) {
+        char* end = nullptr;
+        const double value = strtod(env, &end);
+        if (end == env) break;
+        if (value > 0) w.push_back(value);
+        env = *end == ',' ? end + 1 : end;
+      }
+      return w;
+    }();
+    return weights;
+  }
+
   static int choose_chunks(const ProgramDesc& prog, const soda_cuda_plan* plan,
                            int slices) {
+    if (env_weights().size() > 1 && static_cast<int>(env_weights().size()) <= slices)
+      return static_cast<int>(env_weights().size());
     int reach_lo = 0, reach_hi = 0;
     total_reach(prog, &reach_lo, &reach_hi);
     const int reach = reach_lo + reach_hi;
@@ -1089,7 +1109,17 @@ struct HostPipeline {
     // pipeline chooses by itself.
     std::vector<int> bound(chunks + 1), piece(chunks + 1);
     const bool ramp = plan->host_chunks < 0 && chunks >= 8;
-    if (ramp) {
+    if (static_cast<int>(env_weights().size()) == chunks && chunks > 1) {
+      double total = 0, run = 0;
+      for (double w : env_weights()) total += w;
+      bound[0] = own_lo;
+      for (int k = 0; k < chunks; ++k) {
+        run += env_weights()[k];
+        bound[k + 1] = own_lo + static_cast<int>(slices * (run / total) + 0.5);
+        if (bound[k + 1] <= bound[k]) bound[k + 1] = bound[k] + 1;
+      }
+      bound[chunks] = own_hi;
+    } else if (ramp) {
       // weights 1/4, 1/2, 1 ... 1, 1/2, 1/4 in quarter units
       std::vector<int> weight(chunks, 4);
       weight[0] = weight[chunks - 1] = 1;

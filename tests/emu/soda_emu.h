@@ -59,7 +59,7 @@ inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 // everything is synchronous in the emulation, so streams and events are inert
 typedef void* cudaEvent_t;
-constexpr unsigned cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2;
+constexpr unsigned cudaStreamNonBlocking = 1, cudaEventDefault = 0, cudaEventDisableTiming = 2;
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
   *s = reinterpret_cast<cudaStream_t>(0x1);
   return cudaSuccess;
