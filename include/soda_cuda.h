@@ -83,10 +83,10 @@ typedef struct soda_cuda_opts {
                           * synchronisation is unwanted (e.g. while capturing a CUDA graph) */
   int32_t reserved[5];   /* reserved[0]: chunks of the pipelined host path (copy/compute
                           * overlap of soda_cuda_plan_run_host); 0 = auto, 1 = off,
-                          * n > 1: n equal chunks, -n: n chunks of which the two at
-                          * each end are a quarter and a half as long (less exposed
-                          * copy time at both ends, smaller launches; auto uses equal
-                          * chunks, which measured faster on B200)
+                          * n > 1: n equal chunks, -n: n chunks, each 8 % shorter
+                          * than the one before it (the call ends one chunk's passes
+                          * and download after the last upload, so the last chunk
+                          * should be short; auto does the same with up to 20 chunks)
                           * reserved[1]: soda_cuda_<app> / soda_cuda_run_host split the
                           * grid over this many devices (0 .. n-1) when > 1
                           * (sodac --cuda-gpus; see soda_cuda_multi_run_host) */

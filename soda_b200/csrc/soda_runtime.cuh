@@ -681,6 +681,9 @@ struct soda_cuda_plan {
   // end beyond the local extent: only the global border clips).
   int s_valid_lo[soda::rt::kMaxT];
   int s_valid_hi[soda::rt::kMaxT];
+  // the host pipeline has measured the segment lengths of its chunk windows
+  // (HostPipeline::issue): chunk count and streamed extent it did that for
+  int tuned_chunks, tuned_slices;
 };
 
 namespace soda {
@@ -1003,6 +1006,21 @@ struct HostPipeline {
     return weights;
   }
 
+  // Automatic layout: every chunk is this much shorter than the one before it.
+  // The call ends one chunk's passes and one chunk's download after the last
+  // upload, so the last chunk should be short; a chunk may be at most about
+  // d2h_time / h2d_time (0.92 on B200, both directions busy) of its
+  // predecessor or the downloads queue up behind the uploads.
+  // SODA_CUDA_CHUNK_DECAY overrides (1 = equal chunks).
+  static double auto_decay() {
+    static const double value = [] {
+      const char* env = getenv("SODA_CUDA_CHUNK_DECAY");
+      const double v = env != nullptr ? atof(env) : 0.92;
+      return v > 0.5 && v <= 1.0 ? v : 1.0;
+    }();
+    return value;
+  }
+
   static int choose_chunks(const ProgramDesc& prog, const soda_cuda_plan* plan,
                            int slices) {
     if (env_weights().size() > 1 && static_cast<int>(env_weights().size()) <= slices)
@@ -1017,7 +1035,7 @@ struct HostPipeline {
       bytes += slice_cells * slices * prog.in_elem_bytes[i];
     int chunks = plan->host_chunks;
     if (chunks < 0) {
-      chunks = -chunks;  // this many chunks, shorter at both ends (see issue())
+      chunks = -chunks;  // this many chunks, shrinking towards the end (see issue())
     } else if (chunks == 0) {
       chunks = 1;
       if (bytes >= (32LL << 20)) {
@@ -1030,6 +1048,9 @@ struct HostPipeline {
         chunks = slices / (8 * (reach > 0 ? reach : 1));
         if (chunks > 16) chunks = 16;
         if (chunks < 1) chunks = 1;
+        // the automatic layout shrinks the chunks towards the end (issue()):
+        // a quarter more of them
+        if (chunks >= 8 && auto_decay() < 1.0) chunks += chunks / 4;
       }
     }
     if (chunks > slices) chunks = slices;
@@ -1096,19 +1117,19 @@ struct HostPipeline {
       if (status != SODA_CUDA_OK) return status;
     }
 
-    // chunk bounds: equal chunks, or - a negative chunk count in opts - shorter
-    // chunks at both ends (a quarter, then half of an inner chunk), which
-    // shrinks the upload nothing can overlap (the first) and the download
-    // nothing overlaps (the last).  Measured on B200 for the 16384^2 x 64
-    // workload: 24.40 ms with 16 equal chunks against 24.33 ms ramped on the
-    // same box (profiles/r02_e2e_chunks_tuner_threshold.jsonl) - the copy-out
-    // stream is busy without a gap from the first chunk's compute to the end
-    // of the call, so what remains after the last upload is one inner chunk's
-    // download whatever the sizes of the chunks after it
-    // (profiles/r02_pipeline_trace_summary.txt) - so equal chunks are what the
-    // pipeline chooses by itself.
+    // chunk bounds.  Equal chunks (a positive count in opts), or - the automatic
+    // layout and a negative count - lengths in geometric progression: the
+    // copy-in stream never waits and the copy-out stream runs one chunk
+    // behind it, so the call ends one chunk's passes and one chunk's download
+    // after the last upload and that last chunk should be short.  Measured on
+    // B200 for the 16384^2 x 64 workload (profiles/r02_e2e_chunk_decay.jsonl,
+    // alternating processes on one box): 16 equal chunks 24.1-25.1 ms, 20 chunks
+    // of ratio 0.92 23.8-24.5 ms; ratios 0.90 / 0.94 and 16 / 24 / 28 chunks are
+    // no better.  Shorter chunks at *both* ends (built and measured earlier)
+    // gain nothing: when the first download starts does not matter.
     std::vector<int> bound(chunks + 1), piece(chunks + 1);
-    const bool ramp = plan->host_chunks < 0 && chunks >= 8;
+    const bool decay = plan->host_chunks < 0 ||
+                       (plan->host_chunks == 0 && chunks >= 8 && auto_decay() < 1.0);
     if (static_cast<int>(env_weights().size()) == chunks && chunks > 1) {
       double total = 0, run = 0;
       for (double w : env_weights()) total += w;
@@ -1119,18 +1140,27 @@ struct HostPipeline {
         if (bound[k + 1] <= bound[k]) bound[k + 1] = bound[k] + 1;
       }
       bound[chunks] = own_hi;
-    } else if (ramp) {
-      // weights 1/4, 1/2, 1 ... 1, 1/2, 1/4 in quarter units
-      std::vector<int> weight(chunks, 4);
-      weight[0] = weight[chunks - 1] = 1;
-      weight[1] = weight[chunks - 2] = 2;
-      long long total = 0, run = 0;
-      for (int w : weight) total += w;
+    } else if (decay && chunks > 1) {
+      // in steps of 64 slices where the chunks are long enough (the segment
+      // tuner keeps one measurement per 64 slices of window height); no chunk
+      // shorter than the reach of all passes
+      const double r = auto_decay() < 1.0 ? auto_decay() : 0.92;
+      double total = 0, run = 0, w = 1;
+      for (int k = 0; k < chunks; ++k, w *= r) total += w;
+      const int step = slices >= 64 * 4 * chunks ? 64 : 1;
+      int shortest = std::max(step, reach_lo + reach_hi);
+      if (static_cast<long long>(shortest) * chunks > slices) shortest = slices / chunks;
       bound[0] = own_lo;
-      for (int k = 0; k < chunks; ++k) {
-        run += weight[k];
-        bound[k + 1] = own_lo + static_cast<int>(slices * run / total);
+      w = 1;
+      for (int k = 0; k < chunks; ++k, w *= r) {
+        run += w;
+        int b = own_lo + static_cast<int>(slices * (run / total) / step + 0.5) * step;
+        b = std::max(b, bound[k] + shortest);
+        // what is left must hold the remaining chunks
+        b = std::min(b, own_hi - (chunks - 1 - k) * shortest);
+        bound[k + 1] = b;
       }
+      bound[chunks] = own_hi;
     } else {
       for (int k = 0; k <= chunks; ++k)
         bound[k] = own_lo + static_cast<int>(static_cast<long long>(slices) * k / chunks);
@@ -1139,6 +1169,28 @@ struct HostPipeline {
     // bound plus the reach of all passes), so that chunk k waits for its own
     // piece only, not for the whole upload of chunk k + 1; stretched to what
     // the host holds at both ends
+    // The first call measures the segment length of every chunk window before
+    // anything else is queued (on whatever the plan's arrays hold: every cell
+    // these launches store is stored again below).  Left to the chunks' own
+    // first launches, the measurements would run beside the uploads of the
+    // chunks behind them, which share the HBM with the timed launches.
+    const long long first_window_cells =
+        (dim == 2 ? plan->extent[0]
+                  : static_cast<long long>(plan->extent[0]) * plan->extent[1]) *
+        (bound[1] - bound[0] + reach_lo + reach_hi);
+    if (autotune_enabled() && plan->segment == 0 &&
+        first_window_cells >= tune_min_cells() &&
+        (plan->tuned_chunks != chunks || plan->tuned_slices != slices)) {
+      const long long counted = launch_counter().load();
+      for (int k = 0; k < chunks && status == SODA_CUDA_OK; ++k)
+        status = run_passes_window(plan, plan->d_in, pitches, plan->d_out, pitches,
+                                   bound[k], bound[k + 1]);
+      if (status != SODA_CUDA_OK) return status;
+      SODA_CUDA_CHECK(cudaStreamSynchronize(plan->stream));
+      launch_counter().store(counted);  // tuning, not work
+      plan->tuned_chunks = chunks;
+      plan->tuned_slices = slices;
+    }
     for (int k = 0; k <= chunks; ++k)
       piece[k] = std::min(host_hi, std::max(host_lo, bound[k] + reach_hi));
     piece[0] = host_lo;

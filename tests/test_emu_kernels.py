@@ -103,13 +103,15 @@ def test_pipelined_host_path_under_emulation(name, kwargs):
     ('jacobi2d', dict(extent=(70, 200), time_block=2, iterate=5)),
     ('heat3d', dict(extent=(40, 12, 90), time_block=2, iterate=4,
                     options={'rows': 8})),
-    ('blur', dict(extent=(80, 33), iterate=2)),  # ramped chunks of 1-2 rows
+    ('blur', dict(extent=(80, 33), iterate=2)),  # chunks of a few rows
 ])
-def test_ramped_host_chunks_under_emulation(name, kwargs):
-  """A negative chunk count selects what the pipeline chooses by itself for
-  large grids: shorter chunks at both ends, upload pieces that end where the
-  chunk windows end."""
-  run_case(name, host_chunks=-8, **kwargs)
+@pytest.mark.parametrize('host_chunks', [-8, -3])
+def test_shrinking_host_chunks_under_emulation(name, kwargs, host_chunks):
+  """A negative chunk count selects the layout the pipeline chooses by itself
+  for large grids: every chunk 8 % shorter than the one before it (never
+  shorter than the reach of all passes while the grid allows), upload pieces
+  that end where the chunk windows end."""
+  run_case(name, host_chunks=host_chunks, **kwargs)
 
 
 POW2_2D = '''kernel: pow2_2d

@@ -62,7 +62,7 @@ def test_bench_headline_library_c2():
 
 def test_bench_headline_library_c2_host_pipeline_seams():
   """The chunked H2D / compute / D2H pipeline of the e2e number: windows on
-  the seams between the 16 chunks."""
+  the seams between 16 equal chunks."""
   st, prog = bench.config_program('C2_jacobi2d')
   extent = bench.CONFIGS['C2_jacobi2d']['extent']
   inputs = host_inputs(st, prog, extent)
@@ -73,6 +73,41 @@ def test_bench_headline_library_c2_host_pipeline_seams():
   report = cone.check_host_arrays(st, inputs, outputs, count=2, seed=4,
                                   required=seams)
   assert report['windows'] == 17 and report['bit_exact'], report
+
+
+def automatic_chunk_bounds(slices, reach, chunks=20, ratio=0.92):
+  """The bounds HostPipeline::issue() (soda_runtime.cuh) gives the automatic
+  layout of a grid this large: lengths in geometric progression, in steps of
+  64 slices, none shorter than the reach of all passes."""
+  total = sum(ratio ** k for k in range(chunks))
+  step = 64 if slices >= 64 * 4 * chunks else 1
+  shortest = max(step, reach)
+  bounds, run = [0], 0.0
+  for k in range(chunks):
+    run += ratio ** k
+    b = int(slices * (run / total) / step + 0.5) * step
+    b = max(b, bounds[k] + shortest)
+    b = min(b, slices - (chunks - 1 - k) * shortest)
+    bounds.append(b)
+  bounds[-1] = slices
+  return bounds
+
+
+def test_bench_headline_library_c2_host_pipeline_automatic_layout():
+  """The layout the e2e number runs with (chunk count 0: 20 chunks that
+  shrink towards the end): windows on every seam."""
+  st, prog = bench.config_program('C2_jacobi2d')
+  extent = bench.CONFIGS['C2_jacobi2d']['extent']
+  inputs = host_inputs(st, prog, extent)
+  outputs = {'t0': np.zeros(extent[::-1], dtype=np.float32)}
+  prog.run_host(inputs, outputs, opts=launcher.make_opts(host_chunks=0))
+  bounds = automatic_chunk_bounds(extent[1], 2 * 64)
+  assert len(bounds) == 21 and bounds[1] - bounds[0] > 4 * (bounds[-1] - bounds[-2])
+  seams = [(int(x), b - 32)
+           for b, x in zip(bounds[1:-1], np.linspace(100, 16000, len(bounds) - 2))]
+  report = cone.check_host_arrays(st, inputs, outputs, count=2, seed=5,
+                                  required=seams)
+  assert report['windows'] == len(seams) + 2 and report['bit_exact'], report
 
 
 def test_c1_blur_2000_wide():

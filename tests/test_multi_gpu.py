@@ -159,6 +159,8 @@ def test_default_groups_keep_the_ghost_small():
 @pytest.mark.parametrize('name,extent,world,kwargs', [
     ('jacobi2d', (70, 120), 3, dict(time_block=2, iterate=5, host_chunks=4)),
     ('jacobi2d', (70, 60), 2, dict(time_block=2, iterate=5, host_chunks=1)),
+    # chunks that shrink towards the end (the automatic layout of large grids)
+    ('jacobi2d', (70, 160), 2, dict(time_block=2, iterate=5, host_chunks=-5)),
     ('blur', (300, 60), 2, dict(time_block=1, iterate=3, host_chunks=3)),
     ('denoise2d', (64, 50), 2, dict(host_chunks=2)),
     ('heat3d', (40, 12, 40), 2, dict(time_block=2, iterate=4, host_chunks=3,
