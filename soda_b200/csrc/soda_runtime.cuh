@@ -1045,7 +1045,23 @@ struct HostPipeline {
         // 23.5 / 23.7 / 24.3 / 24.8 ms, the uploads run back to back at 43-47
         // GB/s and lose about 0.07 ms per chunk to the passes' HBM traffic
         // (profiles/r02_e2e_chunks_tuner_threshold.jsonl, r02_pipeline_trace_summary.txt)
-        chunks = slices / (8 * (reach > 0 ? reach : 1));
+        // Redundant compute at the seams is cheap while compute hides under
+        // the copies: an HBM-bound pass moves the grid at ~5 TB/s, the link
+        // moves it at ~50 GB/s each way, so 16 passes may double (chunks as
+        // short as the reach) and still take 0.6 of the copy time.  heat3d
+        // 512^3 x 32 (16 passes, reach 64 of 512 planes): 1 / 4 / 8 chunks 19.7 /
+        // 13.4 / 12.7 ms; jacobi2d 16384^2 x 256 (43 passes): 1 / 4 / 8 chunks
+        // 52.8 / 29.7 / 29.2 ms (profiles/r02_e2e_programs_chunks.jsonl).
+        // SODA_CUDA_CHUNK_REACH overrides the factor (experiments).
+        static const int env_factor = [] {
+          const char* env = getenv("SODA_CUDA_CHUNK_REACH");
+          return env != nullptr ? atoi(env) : 0;
+        }();
+        const int factor =
+            env_factor > 0 ? env_factor
+            : prog.info.num_passes <= 16 ? 1
+            : prog.info.num_passes <= 32 ? 2 : 4;
+        chunks = slices / (factor * (reach > 0 ? reach : 1));
         if (chunks > 16) chunks = 16;
         if (chunks < 1) chunks = 1;
         // the automatic layout shrinks the chunks towards the end (issue()):
