@@ -681,9 +681,6 @@ struct soda_cuda_plan {
   // end beyond the local extent: only the global border clips).
   int s_valid_lo[soda::rt::kMaxT];
   int s_valid_hi[soda::rt::kMaxT];
-  // the host pipeline has measured the segment lengths of its chunk windows
-  // (HostPipeline::issue): chunk count and streamed extent it did that for
-  int tuned_chunks, tuned_slices;
 };
 
 namespace soda {
@@ -1021,6 +1018,22 @@ struct HostPipeline {
     return value;
   }
 
+  // Whether this process has not yet run this chunk layout on this device and
+  // grid (the segment tuner's cache is per process too: the one-shot entry
+  // points make a new plan for every call and must not measure again).
+  static bool first_call_with_layout(const soda_cuda_plan* plan, int chunks,
+                                     int lo, int hi) {
+    static std::mutex mutex;
+    static std::map<std::vector<int>, bool> seen;
+    int device = 0;
+    cudaGetDevice(&device);
+    const std::vector<int> key = {device, plan->extent[0], plan->extent[1],
+                                  plan->extent[2], chunks, lo, hi,
+                                  plan->host_chunks};
+    std::lock_guard<std::mutex> lock(mutex);
+    return seen.emplace(key, true).second;
+  }
+
   static int choose_chunks(const ProgramDesc& prog, const soda_cuda_plan* plan,
                            int slices) {
     if (env_weights().size() > 1 && static_cast<int>(env_weights().size()) <= slices)
@@ -1196,7 +1209,7 @@ struct HostPipeline {
         (bound[1] - bound[0] + reach_lo + reach_hi);
     if (autotune_enabled() && plan->segment == 0 &&
         first_window_cells >= tune_min_cells() &&
-        (plan->tuned_chunks != chunks || plan->tuned_slices != slices)) {
+        first_call_with_layout(plan, chunks, own_lo, own_hi)) {
       const long long counted = launch_counter().load();
       for (int k = 0; k < chunks && status == SODA_CUDA_OK; ++k)
         status = run_passes_window(plan, plan->d_in, pitches, plan->d_out, pitches,
@@ -1204,8 +1217,6 @@ struct HostPipeline {
       if (status != SODA_CUDA_OK) return status;
       SODA_CUDA_CHECK(cudaStreamSynchronize(plan->stream));
       launch_counter().store(counted);  // tuning, not work
-      plan->tuned_chunks = chunks;
-      plan->tuned_slices = slices;
     }
     for (int k = 0; k <= chunks; ++k)
       piece[k] = std::min(host_hi, std::max(host_lo, bound[k] + reach_hi));
