@@ -728,6 +728,8 @@ def run_ours(args, out):
         'ms_per_step': e2e_s * 1e3,
         'host_memory': 'pinned (soda_cuda_host_alloc)',
         'api': 'soda_cuda_plan_run_host (chunked H2D / passes / D2H pipeline)',
+        'chunks': 'automatic: 20 along the streamed dimension, each 8 % shorter '
+                  'than the one before it',
         # the ceiling of this number: both copies at once on this box
         'pcie_peak_gbs': copy_peak['both_gbs'],
         'pcie_h2d_gbs': copy_peak['h2d_gbs'],
@@ -785,6 +787,8 @@ def run_ours(args, out):
         'host_memory': 'pinned (soda_cuda_host_alloc), one slab per rank',
         'api': 'soda_cuda_slab_run_host (per-rank chunked H2D / passes / D2H '
                'pipeline, one NVLink halo exchange per step)',
+        'chunks': 'automatic: 20 per rank along the streamed dimension, each 8 % '
+                  'shorter than the one before it',
         # all ranks copying both ways at the same time on this box
         'pcie_peak_gbs': peak_all,
         'achieved_gbs': nbytes / e2e_s / 1e9,
